@@ -1,0 +1,95 @@
+/*
+ * b200ocl.h -- C ABI of libb200ocl.so: the replay-step hot path of
+ * RaptorMai/online-continual-learning as hand-written sm_100a CUDA.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own (SURVEY.md
+ * section 8b); each entry point below therefore names the reference *Python*
+ * interface whose arithmetic it replaces (file:line under /root/reference).
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, a cudaStream_t passed as void*; no torch types;
+ *   - every pointer is a BORROWED DEVICE pointer, contiguous row-major, owned by
+ *     the caller and kept alive until the stream work completes;
+ *   - fp32 data, int64 labels/indices (the reference's dtypes, data_utils.py:41,
+ *     buffer.py:23);
+ *   - no hidden allocation: scratch is caller-provided, sized by the matching
+ *     *_workspace_bytes() query (must be 256-byte aligned);
+ *   - every function returns 0 on success or a B200OCL_E* code; the message is
+ *     available from b200ocl_last_error() (thread-local); nothing throws;
+ *   - launches are asynchronous on `stream`; no function synchronises.
+ */
+#ifndef B200OCL_H_
+#define B200OCL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200OCL_OK 0
+#define B200OCL_EINVAL 1      /* bad argument (null pointer, negative size, ...)   */
+#define B200OCL_EUNSUPPORTED 2 /* shape outside what the kernels cover            */
+#define B200OCL_EWORKSPACE 3  /* workspace too small or misaligned               */
+#define B200OCL_ECUDA 4       /* a CUDA runtime call failed                      */
+
+#define B200OCL_KNN_MAX_CAND 1024 /* candidates per call of the fused kNN-SV kernel */
+
+const char* b200ocl_last_error(void);
+int b200ocl_version(void);
+/* Number of kernel launches issued through this library since load (bench.py reports it). */
+uint64_t b200ocl_launch_count(void);
+
+/* ---------------------------------------------------------------- kNN Shapley values
+ * Replaces compute_knn_sv minus its network forward: sorted_cand_ind +
+ * euclidean_distance + the Shapley recurrence + scatter (utils/buffer/aser_utils.py:29-59,
+ * 94-116; utils/utils.py:93-95) and the row reductions its callers take
+ * (aser_retrieve.py:79,82,86; aser_update.py:80), in ONE kernel.
+ *   eval_f [E,d] f32, eval_y [E] i64, cand_f [C,d] f32, cand_y [C] i64, k neighbours.
+ * Outputs (each nullable): sv [E,C] Shapley matrix in candidate order; col_sum /
+ * col_max / col_min [C] reductions over eval rows.  Distance is the squared L2 in
+ * direct-difference form; equal distances rank lowest candidate index first.
+ * Reductions are deterministic (fixed-order, no float atomics).  C <= 1024. */
+size_t b200ocl_knn_sv_workspace_bytes(int E, int C, int d);
+int b200ocl_knn_sv(const float* eval_f, const int64_t* eval_y, const float* cand_f, const int64_t* cand_y,
+                   int E, int C, int d, int k,
+                   float* sv, float* col_sum, float* col_max, float* col_min,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- ranking
+ * score[i] = a[i]*sa + (b ? b[i]*sb : 0); idx_out[0..n_out) = positions of the n_out
+ * largest scores in descending order, ties lowest index first (the reference's
+ * sv.argsort(descending=True)[:n], aser_retrieve.py:82-91, aser_update.py:80-93;
+ * MIR's scores.sort(descending=True)[1][:n], mir_retrieve.py:28-29).  n <= 4096.
+ * score_out [n] nullable. */
+int b200ocl_rank_desc(const float* a, float sa, const float* b, float sb, int n,
+                      int64_t* idx_out, int n_out, float* score_out, void* stream);
+
+/* ---------------------------------------------------------------- SupCon loss
+ * Replaces SupConLoss.forward (+ its autograd backward), all-views-anchor mode
+ * (utils/loss.py:19-96): features [B,V,d] f32, labels [B] i64 -> loss[1] and, when
+ * dfeats != NULL, dL/dfeatures [B,V,d].  d <= 1024. */
+size_t b200ocl_supcon_workspace_bytes(int B, int V, int d);
+int b200ocl_supcon(const float* feats, const int64_t* labels, int B, int V, int d, float temperature,
+                   float* loss, float* dfeats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- buffer rows
+ * dst[i,:] = src[idx[i],:]  /  dst[idx[i],:] = src[i,:]   rows of row_bytes bytes
+ * (buffer_img[indices], buffer_img[idx] = x: buffer_utils.py:19-21,115-116;
+ * reservoir_update.py:59-60; aser_update.py:111-112).  row_bytes % 4 == 0.
+ * Scatter with duplicate idx is undefined, as in the reference's index_put. */
+int b200ocl_gather_rows(const void* src, const int64_t* idx, int n_rows, size_t row_bytes, void* dst, void* stream);
+int b200ocl_scatter_rows(const void* src, const int64_t* idx, int n_rows, size_t row_bytes, void* dst, void* stream);
+
+/* ---------------------------------------------------------------- SGD
+ * p -= lr * (g + wd * p) over a flat arena of n floats: torch.optim.SGD without
+ * momentum (utils/setup_elements.py:73-75) and MIR's virtual step
+ * theta' = theta - lr*g when out != p (mir_retrieve.py:43-46).  out may alias p. */
+int b200ocl_sgd_step(const float* p, const float* g, float* out, size_t n, float lr, float wd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200OCL_H_ */

@@ -1,0 +1,55 @@
+"""ctypes binding of the C ABI in include/b200ocl.h.  Fails loudly when the library
+is missing -- there is no fallback path."""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libb200ocl.so')
+
+P = c_void_p
+# name -> (restype, argtypes); one entry per function declared in include/b200ocl.h
+SIGNATURES = {
+    'b200ocl_last_error': (c_char_p, []),
+    'b200ocl_version': (c_int, []),
+    'b200ocl_launch_count': (c_uint64, []),
+    'b200ocl_knn_sv_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'b200ocl_knn_sv': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P]),
+    'b200ocl_rank_desc': (c_int, [P, c_float, P, c_float, c_int, P, c_int, P, P]),
+    'b200ocl_supcon_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'b200ocl_supcon': (c_int, [P, P, c_int, c_int, c_int, c_float, P, P, P, c_size_t, P]),
+    'b200ocl_gather_rows': (c_int, [P, P, c_int, c_size_t, P, P]),
+    'b200ocl_scatter_rows': (c_int, [P, P, c_int, c_size_t, P, P]),
+    'b200ocl_sgd_step': (c_int, [P, P, P, c_size_t, c_float, c_float, P]),
+}
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError('%s is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). '
+                              'b200ocl has no CPU or library fallback.' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().b200ocl_last_error()
+        raise NativeError('%s failed (code %d): %s' % (what, rc, msg.decode() if msg else '?'))
+
+
+def launch_count():
+    return int(lib().b200ocl_launch_count())

@@ -1,0 +1,59 @@
+// common.cuh -- shared helpers for libb200ocl (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/b200ocl.h"
+
+namespace b200ocl {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+int sm_count();
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+#define B200OCL_CHECK_ARG(cond, msg)                      \
+  do {                                                    \
+    if (!(cond)) {                                        \
+      b200ocl::set_error("%s: %s", __func__, msg);        \
+      return B200OCL_EINVAL;                              \
+    }                                                     \
+  } while (0)
+
+#define B200OCL_CUDA(call)                                                                    \
+  do {                                                                                        \
+    cudaError_t err__ = (call);                                                               \
+    if (err__ != cudaSuccess) {                                                               \
+      b200ocl::set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(err__));    \
+      return B200OCL_ECUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+// Count the launch and surface launch-configuration errors immediately.
+#define B200OCL_LAUNCHED()                                                                    \
+  do {                                                                                        \
+    b200ocl::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+    cudaError_t err__ = cudaGetLastError();                                                   \
+    if (err__ != cudaSuccess) {                                                               \
+      b200ocl::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(err__)); \
+      return B200OCL_ECUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+
+}  // namespace b200ocl

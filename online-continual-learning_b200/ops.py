@@ -1,0 +1,167 @@
+"""Tensor-level wrappers over the C ABI (include/b200ocl.h).
+
+Every function takes CUDA torch tensors, hands raw device pointers and the current
+CUDA stream to libb200ocl.so and returns torch tensors.  torch is used for memory and
+streams only.  Non-CUDA inputs raise: there is no CPU path.
+"""
+import torch
+
+from . import _native
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _native.NativeError('b200ocl ops need CUDA tensors (got a %s tensor); there is no CPU fallback'
+                                      % t.device.type)
+
+
+def _f32(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _i64(t):
+    return t.detach().to(torch.int64).contiguous()
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _workspace(nbytes, device):
+    return torch.empty((max(int(nbytes), 256) + 255) // 256 * 256, dtype=torch.uint8, device=device)
+
+
+def knn_sv(eval_f, eval_y, cand_f, cand_y, k, want_matrix=False, want_sum=True, want_max=False, want_min=False):
+    """Fused kNN Shapley values on feature matrices.
+
+    Mirrors compute_knn_sv + its callers' row reductions
+    (reference utils/buffer/aser_utils.py:29-59; aser_retrieve.py:79-86; aser_update.py:80).
+    Returns dict with any of 'sv' [E,C], 'sum' [C], 'max' [C], 'min' [C]."""
+    _need_cuda(eval_f, eval_y, cand_f, cand_y)
+    eval_f, cand_f, eval_y, cand_y = _f32(eval_f), _f32(cand_f), _i64(eval_y), _i64(cand_y)
+    if eval_f.dim() != 2 or cand_f.dim() != 2 or eval_f.shape[1] != cand_f.shape[1]:
+        raise ValueError('eval_f [E,d] and cand_f [C,d] must share d')
+    E, d = eval_f.shape
+    C = cand_f.shape[0]
+    if eval_y.numel() != E or cand_y.numel() != C:
+        raise ValueError('label count does not match feature count')
+    dev = eval_f.device
+    out = {}
+    sv = torch.empty((E, C), dtype=torch.float32, device=dev) if want_matrix else None
+    cs = torch.empty(C, dtype=torch.float32, device=dev) if want_sum else None
+    cx = torch.empty(C, dtype=torch.float32, device=dev) if want_max else None
+    cn = torch.empty(C, dtype=torch.float32, device=dev) if want_min else None
+    L = _native.lib()
+    ws_bytes = L.b200ocl_knn_sv_workspace_bytes(E, C, d)
+    ws = _workspace(ws_bytes, dev)
+    rc = L.b200ocl_knn_sv(_ptr(eval_f), _ptr(eval_y), _ptr(cand_f), _ptr(cand_y), E, C, d, int(k),
+                          _ptr(sv), _ptr(cs), _ptr(cx), _ptr(cn), _ptr(ws), ws.numel(), _stream())
+    _native.check(rc, 'b200ocl_knn_sv')
+    if want_matrix:
+        out['sv'] = sv
+    if want_sum:
+        out['sum'] = cs
+    if want_max:
+        out['max'] = cx
+    if want_min:
+        out['min'] = cn
+    return out
+
+
+def rank_desc(a, n_out=None, sa=1.0, b=None, sb=0.0, return_scores=False):
+    """Indices of the n_out largest entries of a*sa + b*sb, descending, ties lowest index
+    first (sv.argsort(descending=True)[:n], aser_retrieve.py:88-91)."""
+    _need_cuda(a, b)
+    a = _f32(a).reshape(-1)
+    n = a.numel()
+    if b is not None:
+        b = _f32(b).reshape(-1)
+        if b.numel() != n:
+            raise ValueError('a and b differ in length')
+    n_out = n if n_out is None else min(int(n_out), n)
+    idx = torch.empty(n_out, dtype=torch.int64, device=a.device)
+    sc = torch.empty(n, dtype=torch.float32, device=a.device) if return_scores else None
+    rc = _native.lib().b200ocl_rank_desc(_ptr(a), float(sa), _ptr(b), float(sb), n, _ptr(idx), n_out, _ptr(sc),
+                                         _stream())
+    _native.check(rc, 'b200ocl_rank_desc')
+    return (idx, sc) if return_scores else idx
+
+
+def supcon(features, labels, temperature, need_grad=True):
+    """Fused SupCon loss (+ gradient w.r.t. features).  features [B,V,...], labels [B].
+    Returns (loss[1] tensor, dfeatures or None).  utils/loss.py:19-96."""
+    _need_cuda(features, labels)
+    if features.dim() < 3:
+        raise ValueError('`features` needs to be [bsz, n_views, ...],at least 3 dimensions are required')
+    B, V = features.shape[0], features.shape[1]
+    f = _f32(features).reshape(B, V, -1)
+    labels = _i64(labels).reshape(-1)
+    if labels.shape[0] != B:
+        raise ValueError('Num of labels does not match num of features')
+    d = f.shape[2]
+    loss = torch.empty(1, dtype=torch.float32, device=f.device)
+    grad = torch.empty_like(f) if need_grad else None
+    L = _native.lib()
+    ws = _workspace(L.b200ocl_supcon_workspace_bytes(B, V, d), f.device)
+    rc = L.b200ocl_supcon(_ptr(f), _ptr(labels), B, V, d, float(temperature), _ptr(loss), _ptr(grad), _ptr(ws),
+                          ws.numel(), _stream())
+    _native.check(rc, 'b200ocl_supcon')
+    return loss, grad
+
+
+def gather_rows(src, idx, out=None):
+    """out[i] = src[idx[i]] over the first dimension (buffer_img[indices])."""
+    _need_cuda(src, idx, out)
+    if not src.is_contiguous():
+        raise ValueError('src must be contiguous')
+    idx = _i64(idx).reshape(-1)
+    n = idx.numel()
+    row_bytes = src[0].numel() * src.element_size() if src.shape[0] > 0 else 0
+    if out is None:
+        out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    elif not out.is_contiguous() or out.dtype != src.dtype or out.shape[0] < n:
+        raise ValueError('bad out tensor')
+    if n == 0 or row_bytes == 0:
+        return out
+    rc = _native.lib().b200ocl_gather_rows(_ptr(src), _ptr(idx), n, row_bytes, _ptr(out), _stream())
+    _native.check(rc, 'b200ocl_gather_rows')
+    return out
+
+
+def scatter_rows(dst, idx, src):
+    """dst[idx[i]] = src[i] over the first dimension (buffer_img[idx] = x)."""
+    _need_cuda(dst, idx, src)
+    if not dst.is_contiguous():
+        raise ValueError('dst must be contiguous')
+    idx = _i64(idx).reshape(-1)
+    n = idx.numel()
+    if n == 0:
+        return dst
+    src = src.detach().to(dst.dtype).contiguous()
+    row_bytes = dst[0].numel() * dst.element_size()
+    if src.numel() * src.element_size() != n * row_bytes:
+        raise ValueError('src does not hold len(idx) rows of dst')
+    rc = _native.lib().b200ocl_scatter_rows(_ptr(src), _ptr(idx), n, row_bytes, _ptr(dst), _stream())
+    _native.check(rc, 'b200ocl_scatter_rows')
+    return dst
+
+
+def sgd_step(param, grad, lr, weight_decay=0.0, out=None):
+    """out = param - lr*(grad + wd*param) over flat fp32 arenas; out defaults to param (in place)."""
+    _need_cuda(param, grad, out)
+    if out is None:
+        out = param
+    for t in (param, grad, out):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError('sgd_step needs contiguous fp32 tensors')
+    if grad.numel() != param.numel() or out.numel() != param.numel():
+        raise ValueError('size mismatch')
+    rc = _native.lib().b200ocl_sgd_step(_ptr(param), _ptr(grad), _ptr(out), param.numel(), float(lr),
+                                        float(weight_decay), _stream())
+    _native.check(rc, 'b200ocl_sgd_step')
+    return out
