@@ -89,6 +89,81 @@ int b200ocl_scatter_rows(const void* src, const int64_t* idx, int n_rows, size_t
  * theta' = theta - lr*g when out != p (mir_retrieve.py:43-46).  out may alias p. */
 int b200ocl_sgd_step(const float* p, const float* g, float* out, size_t n, float lr, float wd, void* stream);
 
+
+/* ---------------------------------------------------------------- Reduced-ResNet18 engine
+ * The only network on the replay-step path (models/resnet.py:14-37,69-116 BasicBlock ResNet
+ * with nf=20; :140-168 SupConResNet; per-dataset classifier, utils/setup_elements.py:46-68).
+ *   head: 0 classifier (logits [N,num_classes]); 1/2/3 SupConResNet with 'linear'/'mlp'/'None'
+ *   head (L2-normalised projection [N,feat_dim]).
+ * State = flat arenas owned by the caller:
+ *   params / grads  every learnable tensor in torch parameters() order and torch layout
+ *                   (a reference nn.Module can alias its Parameters onto it);
+ *   packed          kernel-layout copies of the conv weights, refreshed by b200ocl_net_pack /
+ *                   b200ocl_net_sgd_step;
+ *   bn_stats        per BatchNorm2d running_mean[c], running_var[c] in module order;
+ *   bn_tracked      num_batches_tracked per BatchNorm2d.
+ * Images are fp32 NCHW [N,3,H,W] exactly as the reference feeds them (no normalisation,
+ * setup_elements.py:29-43); activations are NHWC inside the engine. */
+typedef struct {
+  int in_h, in_w;      /* 32x32 CIFAR, 84x84 Mini-ImageNet (setup_elements.py:11-17) */
+  int nf;              /* 20 (Reduced_ResNet18, resnet.py:112-116) */
+  int num_classes;     /* classifier width when head == 0 */
+  int head;            /* 0 classifier | 1 linear | 2 mlp | 3 none */
+  int feat_dim;        /* SupCon projection size (128) */
+} b200ocl_net_desc;
+
+typedef struct {
+  float* params;
+  float* grads;
+  float* packed;
+  float* bn_stats;
+  int64_t* bn_tracked;
+} b200ocl_net_state;
+
+/* Sizes (in elements) of the arenas and basic shape facts. */
+typedef struct {
+  size_t n_params, n_packed, n_bn_stats;
+  int n_bn, n_tensors, dim_in, out_dim;
+} b200ocl_net_info;
+int b200ocl_net_query(const b200ocl_net_desc* desc, b200ocl_net_info* info);
+/* i-th parameter tensor in parameters() order: offset/numel in the arena, has_grad = 0 for the
+ * SupConResNet encoder classifier that never receives a gradient. */
+int b200ocl_net_tensor(const b200ocl_net_desc* desc, int i, size_t* offset, size_t* numel, int* has_grad);
+
+/* packed <- params (call after loading weights). */
+int b200ocl_net_pack(const b200ocl_net_desc* desc, const b200ocl_net_state* st, void* stream);
+
+/* model.eval(); model.features(x) under no_grad (utils/utils.py:45-90): feat [N,dim_in]. */
+size_t b200ocl_net_eval_workspace_bytes(const b200ocl_net_desc* desc, int N);
+int b200ocl_net_features_eval(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
+                              float* feat, void* workspace, size_t workspace_bytes, void* stream);
+
+/* model.train(); out = model.forward(x): batch-statistics BN, running stats and
+ * num_batches_tracked updated (momentum 0.1, unbiased variance); activations are kept in
+ * `workspace` for b200ocl_net_backward.  out [N,out_dim]. */
+size_t b200ocl_net_train_workspace_bytes(const b200ocl_net_desc* desc, int N);
+int b200ocl_net_forward_train(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
+                              float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* loss.backward() for the forward kept in `workspace`: dout [N,out_dim] -> st->grads
+ * (overwritten, or added to when accumulate != 0 -- exp_replay.py:55,77 accumulate two
+ * backward passes before one opt.step()). */
+int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* dout, int N,
+                         void* workspace, size_t workspace_bytes, int accumulate, void* stream);
+
+/* opt.step() of torch.optim.SGD without momentum over every tensor that has a gradient
+ * (setup_elements.py:73-75), then refresh `packed`.  With dst != NULL the updated weights go
+ * to dst->params / dst->packed instead (MIR's virtual step theta - lr*grad on a copy,
+ * mir_retrieve.py:34-47); tensors without gradient are copied. */
+int b200ocl_net_sgd_step(const b200ocl_net_desc* desc, const b200ocl_net_state* st, float lr, float weight_decay,
+                         const b200ocl_net_state* dst, void* stream);
+
+/* Mean cross-entropy (agents/base.py:95,113) over logits [N,C], labels [N]:
+ * loss[1]; per_sample [N] (F.cross_entropy(reduction='none'), mir_retrieve.py:26-27);
+ * dlogits [N,C] = d(mean CE)/dlogits; n_correct[1] = #(argmax == label).  Each output nullable. */
+int b200ocl_ce_loss(const float* logits, const int64_t* labels, int N, int C, float* loss, float* per_sample,
+                    float* dlogits, int64_t* n_correct, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,17 @@ SIGNATURES = {
     'b200ocl_gather_rows': (c_int, [P, P, c_int, c_size_t, P, P]),
     'b200ocl_scatter_rows': (c_int, [P, P, c_int, c_size_t, P, P]),
     'b200ocl_sgd_step': (c_int, [P, P, P, c_size_t, c_float, c_float, P]),
+    # ResNet engine: descriptor / state / info structs are passed by pointer (see engine.py)
+    'b200ocl_net_query': (c_int, [P, P]),
+    'b200ocl_net_tensor': (c_int, [P, c_int, P, P, P]),
+    'b200ocl_net_pack': (c_int, [P, P, P]),
+    'b200ocl_net_eval_workspace_bytes': (c_size_t, [P, c_int]),
+    'b200ocl_net_features_eval': (c_int, [P, P, P, c_int, P, P, c_size_t, P]),
+    'b200ocl_net_train_workspace_bytes': (c_size_t, [P, c_int]),
+    'b200ocl_net_forward_train': (c_int, [P, P, P, c_int, P, P, c_size_t, P]),
+    'b200ocl_net_backward': (c_int, [P, P, P, c_int, P, c_size_t, c_int, P]),
+    'b200ocl_net_sgd_step': (c_int, [P, P, c_float, c_float, P, P]),
+    'b200ocl_ce_loss': (c_int, [P, P, c_int, c_int, P, P, P, P, P]),
 }
 
 _lib = None

@@ -27,6 +27,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
   do {                                                                                        \
     cudaError_t err__ = (call);                                                               \
     if (err__ != cudaSuccess) {                                                               \
+      (void)cudaGetLastError(); /* clear the non-sticky error state */                        \
       b200ocl::set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(err__));    \
       return B200OCL_ECUDA;                                                                   \
     }                                                                                         \

@@ -1,0 +1,406 @@
+// conv.cu -- fp32 implicit-GEMM convolution for the Reduced-ResNet18 blocks (sm_100a).
+//
+// One kernel serves the forward 3x3 / 1x1 convolutions (stride 1 or 2), their eval-mode
+// variant with BatchNorm folded into the epilogue (+ReLU, +residual), their train-mode variant
+// that also produces the batch statistics, and the data-gradient convolutions (transposed
+// gather, optional accumulate).  Replaces the cuDNN calls behind nn.Conv2d / nn.BatchNorm2d
+// in reference models/resnet.py:11-12,20-36,73-74.
+//
+// fp32 on the CUDA cores, not TF32 tensor cores, on purpose: ASER ranks buffer samples by
+// nearest neighbours in this network's feature space and the parity bar is bit-exact
+// retrieved / evicted indices (BASELINE.json north_star); 10-bit-mantissa products move the
+// features by ~1e-3 relative and reorder neighbours.  (A 3xTF32 split on tcgen05 is the
+// planned tensor-core path; see DESIGN.md.)
+//
+// Tiling: GEMM M = output pixels, N = output channels, K = taps x input channels.
+//   CTA = 4 warps; a warp owns 32*PT pixels x 20 channels, a thread PT pixels x 20 channels
+//   (lanes = consecutive pixels, so the 20 weights of a k are a broadcast LDS.128 x5 and the
+//   activations a conflict-free LDS.128 per 4 k);  BN in {20,40,80} channels per CTA,
+//   BM = (80/BN)*32*PT pixels;  K advances one (tap, 20-channel) chunk at a time through a
+//   two-stage cp.async pipeline with zero-fill for the padding halo.
+#include "conv.cuh"
+
+namespace b200ocl {
+namespace {
+
+constexpr int CONV_THREADS = 128;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const unsigned int s = static_cast<unsigned int>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+
+// Shared epilogue: thread holds acc[PT][20] for rows r = row_base + 32*p (p < PT) and
+// channels n0 + wn*20 .. +19.  `scratch` is >= 4*20*2 doubles of shared memory, free to use.
+template <int BN, int PT>
+__device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT][20], int m0, int n0, int row_base,
+                                              int wm, int wn, int lane, int tid, double* scratch) {
+  constexpr int WN = BN / 20, WM = 4 / WN;
+  const int cbase = n0 + wn * 20;
+  if (a.mode == CONV_EVAL) {
+    float sc[20], mu[20], be[20];
+#pragma unroll
+    for (int c = 0; c < 20; ++c) {
+      const float inv = 1.0f / sqrtf(a.rvar[cbase + c] + a.eps);
+      sc[c] = inv * a.gamma[cbase + c];
+      mu[c] = a.rmean[cbase + c];
+      be[c] = a.beta[cbase + c];
+    }
+#pragma unroll
+    for (int p = 0; p < PT; ++p) {
+      const int m = m0 + row_base + 32 * p;
+      if (m >= a.M) continue;
+      float* o = a.out + (size_t)m * a.CN + cbase;
+      const float* rs = a.residual ? a.residual + (size_t)m * a.CN + cbase : nullptr;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        float4 v;
+        v.x = (acc[p][4 * j + 0] - mu[4 * j + 0]) * sc[4 * j + 0] + be[4 * j + 0];
+        v.y = (acc[p][4 * j + 1] - mu[4 * j + 1]) * sc[4 * j + 1] + be[4 * j + 1];
+        v.z = (acc[p][4 * j + 2] - mu[4 * j + 2]) * sc[4 * j + 2] + be[4 * j + 2];
+        v.w = (acc[p][4 * j + 3] - mu[4 * j + 3]) * sc[4 * j + 3] + be[4 * j + 3];
+        if (rs) {
+          const float4 r4 = *reinterpret_cast<const float4*>(rs + 4 * j);
+          v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+        }
+        if (a.relu) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(o + 4 * j) = v;
+      }
+    }
+    return;
+  }
+  // RAW / TRAIN / ACCUM: store (or add) the accumulators
+#pragma unroll
+  for (int p = 0; p < PT; ++p) {
+    const int m = m0 + row_base + 32 * p;
+    if (m >= a.M) continue;
+    float* o = a.out + (size_t)m * a.CN + cbase;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      float4 v = make_float4(acc[p][4 * j], acc[p][4 * j + 1], acc[p][4 * j + 2], acc[p][4 * j + 3]);
+      if (a.mode == CONV_ACCUM) {
+        const float4 old = *reinterpret_cast<const float4*>(o + 4 * j);
+        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+      }
+      *reinterpret_cast<float4*>(o + 4 * j) = v;
+    }
+  }
+  if (a.mode != CONV_TRAIN) return;
+
+  // ---- batch statistics: fp64 sums, fixed order (thread -> warp shuffle -> warps -> CTAs)
+  double* s_stat = scratch;  // [WM][BN][2]
+#pragma unroll
+  for (int c = 0; c < 20; ++c) {
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int p = 0; p < PT; ++p) {
+      const int m = m0 + row_base + 32 * p;
+      if (m < a.M) {
+        const double v = (double)acc[p][c];
+        s += v;
+        q += v * v;
+      }
+    }
+    s = warp_sum_d(s);
+    q = warp_sum_d(q);
+    if (lane == 0) {
+      s_stat[((wm * BN) + wn * 20 + c) * 2 + 0] = s;
+      s_stat[((wm * BN) + wn * 20 + c) * 2 + 1] = q;
+    }
+  }
+  __syncthreads();
+  if (tid < BN) {
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int w = 0; w < WM; ++w) {
+      s += s_stat[((w * BN) + tid) * 2 + 0];
+      q += s_stat[((w * BN) + tid) * 2 + 1];
+    }
+    double* dst = a.stat_part + ((size_t)blockIdx.x * a.CN + n0 + tid) * 2;
+    dst[0] = s;
+    dst[1] = q;
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ bool is_last;
+  if (tid == 0) is_last = (atomicAdd(a.counter + blockIdx.y, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // all 128 threads: channel = tid % BN, CTA-partials strided by 128/BN groups, then fixed-order combine
+  constexpr int GROUPS = CONV_THREADS / BN;  // 6, 3 or 1
+  const int ch = tid % BN, grp = tid / BN;
+  double s = 0.0, q = 0.0;
+  if (grp < GROUPS) {
+    for (unsigned int b = grp; b < gridDim.x; b += GROUPS) {
+      const double* src = a.stat_part + ((size_t)b * a.CN + n0 + ch) * 2;
+      s += __ldcg(src);
+      q += __ldcg(src + 1);
+    }
+  }
+  __syncthreads();  // s_stat reuse
+  double* s_fin = scratch;  // [GROUPS][BN][2]
+  if (grp < GROUPS) {
+    s_fin[(grp * BN + ch) * 2 + 0] = s;
+    s_fin[(grp * BN + ch) * 2 + 1] = q;
+  }
+  __syncthreads();
+  if (tid < BN) {
+    double S = 0.0, Q = 0.0;
+    for (int g = 0; g < GROUPS; ++g) {
+      S += s_fin[(g * BN + tid) * 2 + 0];
+      Q += s_fin[(g * BN + tid) * 2 + 1];
+    }
+    const double cnt = (double)a.M;
+    const double mean = S / cnt;
+    double var = Q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const int c = n0 + tid;
+    a.save_mean[c] = (float)mean;
+    a.save_invstd[c] = (float)(1.0 / sqrt(var + (double)a.eps));
+    const double unbiased = (a.M > 1) ? var * cnt / (cnt - 1.0) : var;
+    a.run_mean[c] = (1.f - a.momentum) * a.run_mean[c] + a.momentum * (float)mean;
+    a.run_var[c] = (1.f - a.momentum) * a.run_var[c] + a.momentum * (float)unbiased;
+  }
+}
+
+template <int BN, int PT>
+__global__ void __launch_bounds__(CONV_THREADS) conv_kernel(ConvArgs a) {
+  constexpr int WN = BN / 20, WM = 4 / WN, BM = WM * 32 * PT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sA = reinterpret_cast<float*>(smem_raw);  // [2][BM][20]
+  float* sB = sA + 2 * BM * 20;                    // [2][20][BN]
+  int* s_base = reinterpret_cast<int*>(sB + 2 * 20 * BN);
+  int* s_h0 = s_base + BM;
+  int* s_w0 = s_h0 + BM;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp / WN, wn = warp % WN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int hw_out = a.Hout * a.Wout;
+
+  for (int r = tid; r < BM; r += CONV_THREADS) {
+    const int m = m0 + r;
+    if (m < a.M) {
+      const int n = m / hw_out, rem = m - n * hw_out;
+      const int ho = rem / a.Wout, wo = rem - ho * a.Wout;
+      s_base[r] = n * a.Hin * a.Win;
+      s_h0[r] = a.transposed ? ho + a.pad : ho * a.stride - a.pad;
+      s_w0[r] = a.transposed ? wo + a.pad : wo * a.stride - a.pad;
+    } else {
+      s_base[r] = 0;
+      s_h0[r] = -(1 << 20);
+      s_w0[r] = -(1 << 20);
+    }
+  }
+  __syncthreads();
+
+  const int cpk = a.CK / 20;
+  const int nchunks = a.ks * a.ks * cpk;
+
+  auto load_chunk = [&](int c, int buf) {
+    const int tap = c / cpk, ci0 = (c - tap * cpk) * 20;
+    const int kh = tap / a.ks, kw = tap - kh * a.ks;
+    float* dA = sA + buf * BM * 20;
+    for (int idx = tid; idx < BM * 5; idx += CONV_THREADS) {
+      const int r = idx / 5, q = idx - r * 5;
+      int hi, wi;
+      bool ok;
+      if (!a.transposed) {
+        hi = s_h0[r] + kh;
+        wi = s_w0[r] + kw;
+        ok = (unsigned)hi < (unsigned)a.Hin && (unsigned)wi < (unsigned)a.Win;
+      } else {
+        const int th = s_h0[r] - kh, tw = s_w0[r] - kw;
+        ok = (th >= 0) && (tw >= 0);
+        if (a.stride == 2) {
+          ok = ok && (((th | tw) & 1) == 0);
+          hi = th >> 1;
+          wi = tw >> 1;
+        } else {
+          hi = th;
+          wi = tw;
+        }
+        ok = ok && hi < a.Hin && wi < a.Win;
+      }
+      const float* src = ok ? a.in + ((size_t)(s_base[r] + hi * a.Win + wi) * a.CK + ci0 + q * 4) : a.in;
+      cp_async16(dA + r * 20 + q * 4, src, ok ? 16 : 0);
+    }
+    float* dB = sB + buf * 20 * BN;
+    const float* wsrc = a.w + ((size_t)tap * a.CK + ci0) * a.CN + n0;
+    for (int idx = tid; idx < 20 * (BN / 4); idx += CONV_THREADS) {
+      const int kk = idx / (BN / 4), q = idx - kk * (BN / 4);
+      cp_async16(dB + kk * BN + q * 4, wsrc + (size_t)kk * a.CN + q * 4, 16);
+    }
+  };
+
+  float acc[PT][20];
+#pragma unroll
+  for (int p = 0; p < PT; ++p)
+#pragma unroll
+    for (int c = 0; c < 20; ++c) acc[p][c] = 0.f;
+
+  const int row_base = wm * 32 * PT + lane;
+  load_chunk(0, 0);
+  cp_async_commit();
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    if (c + 1 < nchunks) {
+      load_chunk(c + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* pA = sA + buf * BM * 20 + row_base * 20;
+    const float* pB = sB + buf * 20 * BN + wn * 20;
+#pragma unroll
+    for (int k4 = 0; k4 < 5; ++k4) {
+      float4 av[PT];
+#pragma unroll
+      for (int p = 0; p < PT; ++p) av[p] = *reinterpret_cast<const float4*>(pA + p * 32 * 20 + k4 * 4);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float w[20];
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          *reinterpret_cast<float4*>(&w[4 * j]) = *reinterpret_cast<const float4*>(pB + (k4 * 4 + kk) * BN + 4 * j);
+#pragma unroll
+        for (int p = 0; p < PT; ++p) {
+          const float x = kk == 0 ? av[p].x : (kk == 1 ? av[p].y : (kk == 2 ? av[p].z : av[p].w));
+#pragma unroll
+          for (int cc = 0; cc < 20; ++cc) acc[p][cc] = fmaf(x, w[cc], acc[p][cc]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  conv_epilogue<BN, PT>(a, acc, m0, n0, row_base, wm, wn, lane, tid, reinterpret_cast<double*>(smem_raw));
+}
+
+// Stem: 3 -> 20 channels, 3x3, stride 1, pad 1, NCHW input read directly (no layout pass).
+// One thread per output pixel, 27 x 20 weights broadcast from shared memory.
+__global__ void __launch_bounds__(CONV_THREADS) stem_kernel(ConvArgs a) {
+  __shared__ __align__(16) float sW[27 * 20];
+  __shared__ __align__(16) double scratch[4 * 20 * 2 * 2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 27 * 20; i += CONV_THREADS) sW[i] = a.w[i];
+  __syncthreads();
+  const int m0 = blockIdx.x * CONV_THREADS;
+  const int m = m0 + tid;
+  float acc[1][20];
+#pragma unroll
+  for (int c = 0; c < 20; ++c) acc[0][c] = 0.f;
+  if (m < a.M) {
+    const int hw = a.Hin * a.Win;
+    const int n = m / hw, rem = m - n * hw;
+    const int ho = rem / a.Win, wo = rem - ho * a.Win;
+    const float* xin = a.in + (size_t)n * 3 * hw;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = ho + kh - 1;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = wo + kw - 1;
+        const bool ok = (unsigned)hi < (unsigned)a.Hin && (unsigned)wi < (unsigned)a.Win;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float x = ok ? __ldg(xin + (size_t)ci * hw + hi * a.Win + wi) : 0.f;
+          const float* w = sW + ((kh * 3 + kw) * 3 + ci) * 20;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const float4 w4 = *reinterpret_cast<const float4*>(w + 4 * j);
+            acc[0][4 * j + 0] = fmaf(x, w4.x, acc[0][4 * j + 0]);
+            acc[0][4 * j + 1] = fmaf(x, w4.y, acc[0][4 * j + 1]);
+            acc[0][4 * j + 2] = fmaf(x, w4.z, acc[0][4 * j + 2]);
+            acc[0][4 * j + 3] = fmaf(x, w4.w, acc[0][4 * j + 3]);
+          }
+        }
+      }
+    }
+  }
+  // BN = 20, PT = 1: warp w owns rows 32*w + lane  (WM = 4, WN = 1)
+  conv_epilogue<20, 1>(a, acc, m0, 0, warp * 32 + lane, warp, 0, lane, tid, scratch);
+}
+
+template <int BN, int PT>
+int launch_conv_cfg(const ConvArgs& a, cudaStream_t stream) {
+  constexpr int WN = BN / 20, WM = 4 / WN, BM = WM * 32 * PT;
+  constexpr size_t smem = (size_t)(2 * BM * 20 + 2 * 20 * BN) * sizeof(float) + 3 * BM * sizeof(int);
+  static bool configured = false;
+  if (!configured) {
+    B200OCL_CUDA(cudaFuncSetAttribute(conv_kernel<BN, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((a.M + BM - 1) / BM, a.CN / BN);
+  conv_kernel<BN, PT><<<grid, CONV_THREADS, smem, stream>>>(a);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
+
+}  // namespace
+
+int conv_max_grid_m(int M) { return (M + 31) / 32; }
+
+int launch_conv(const ConvArgs& a, cudaStream_t stream) {
+  if (a.CK % 20 != 0 || a.CN % 20 != 0 || a.M <= 0) {
+    set_error("launch_conv: channel counts must be multiples of 20 (CK=%d CN=%d M=%d)", a.CK, a.CN, a.M);
+    return B200OCL_EUNSUPPORTED;
+  }
+  // Pick (BN, PT): the largest tile that still gives >= 2 CTAs per SM; otherwise the tiling with most CTAs.
+  const int target = 2 * sm_count();
+  const int bns[3] = {80, 40, 20};
+  const int pts[3] = {4, 2, 1};
+  int best_bn = 20, best_pt = 1;
+  long best_ctas = -1;
+  bool found = false;
+  for (int bi = 0; bi < 3 && !found; ++bi) {
+    const int bn = bns[bi];
+    if (a.CN % bn) continue;
+    for (int pi = 0; pi < 3; ++pi) {
+      const int pt = pts[pi];
+      const int bm = (80 / bn) * 32 * pt;
+      const long ctas = (long)((a.M + bm - 1) / bm) * (a.CN / bn);
+      if (ctas >= target) {
+        best_bn = bn; best_pt = pt; found = true;
+        break;
+      }
+      if (ctas > best_ctas) {
+        best_ctas = ctas; best_bn = bn; best_pt = pt;
+      }
+    }
+  }
+#define B200OCL_CONV_CASE(BN_, PT_) \
+  if (best_bn == BN_ && best_pt == PT_) return launch_conv_cfg<BN_, PT_>(a, stream)
+  B200OCL_CONV_CASE(80, 4); B200OCL_CONV_CASE(80, 2); B200OCL_CONV_CASE(80, 1);
+  B200OCL_CONV_CASE(40, 4); B200OCL_CONV_CASE(40, 2); B200OCL_CONV_CASE(40, 1);
+  B200OCL_CONV_CASE(20, 4); B200OCL_CONV_CASE(20, 2); B200OCL_CONV_CASE(20, 1);
+#undef B200OCL_CONV_CASE
+  return B200OCL_EUNSUPPORTED;
+}
+
+int launch_stem(const ConvArgs& a, cudaStream_t stream) {
+  if (a.CK != 3 || a.CN != 20 || a.ks != 3 || a.stride != 1 || a.Hin != a.Hout || a.Win != a.Wout) {
+    set_error("launch_stem: only the 3->20 3x3 stride-1 stem is supported");
+    return B200OCL_EUNSUPPORTED;
+  }
+  stem_kernel<<<(a.M + CONV_THREADS - 1) / CONV_THREADS, CONV_THREADS, 0, stream>>>(a);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
+
+}  // namespace b200ocl

@@ -1,0 +1,48 @@
+// conv.cuh -- argument block and launchers of the implicit-GEMM convolution kernels.
+#pragma once
+#include "common.cuh"
+
+namespace b200ocl {
+
+enum ConvMode {
+  CONV_RAW = 0,    // out = acc
+  CONV_EVAL = 1,   // out = relu?((acc - rmean) * gamma/sqrt(rvar+eps) + beta (+ residual))   (folded eval-mode BN)
+  CONV_TRAIN = 2,  // out = acc, plus per-channel batch statistics (sum, sum of squares) -> mean/invstd,
+                   // running-stat update by the last CTA of each channel tile
+  CONV_ACCUM = 3   // out += acc (data-gradient merged into an existing gradient)
+};
+
+struct ConvArgs {
+  const float* in;   // NHWC [N,Hin,Win,CK]   (stem: NCHW [N,3,Hin,Win])
+  const float* w;    // packed [ks*ks][CK][CN]
+  float* out;        // NHWC [N,Hout,Wout,CN]
+  int N, Hin, Win, CK, Hout, Wout, CN;
+  int ks, stride, pad;
+  int transposed;    // 0: forward gather (hi = ho*stride - pad + kh); 1: data-gradient gather
+                     //    (input pixel (t/stride) with t = ho + pad - kh, only when divisible)
+  int M;             // N*Hout*Wout output pixels
+  int mode;
+  // CONV_EVAL
+  const float* gamma;
+  const float* beta;
+  const float* rmean;
+  const float* rvar;
+  const float* residual;  // NHWC like out, nullable
+  int relu;
+  float eps;
+  // CONV_TRAIN
+  double* stat_part;       // [gridDim.x][CN][2]
+  unsigned int* counter;   // [gridDim.y], zeroed before the forward pass
+  float* save_mean;
+  float* save_invstd;
+  float* run_mean;
+  float* run_var;
+  float momentum;
+};
+
+// Upper bound of gridDim.x over every tiling launch_conv may choose (sizes stat_part).
+int conv_max_grid_m(int M);
+int launch_conv(const ConvArgs& a, cudaStream_t stream);   // CK, CN multiples of 20
+int launch_stem(const ConvArgs& a, cudaStream_t stream);   // CK == 3, CN == 20, ks == 3, NCHW input
+
+}  // namespace b200ocl

@@ -245,7 +245,7 @@ int b200ocl_supcon(const float* feats, const int64_t* labels, int B, int V, int 
   B200OCL_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
   static bool configured = false;
   if (!configured) {
-    const int max_smem = 227 * 1024;
+    const int max_smem = 200 * 1024;  // d = 1024 needs 165 KB; static smem takes a little of the 227 KB
     B200OCL_CUDA(cudaFuncSetAttribute(supcon_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     B200OCL_CUDA(cudaFuncSetAttribute(supcon_grad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     B200OCL_CUDA(cudaFuncSetAttribute(supcon_grad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
