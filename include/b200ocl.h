@@ -145,11 +145,11 @@ size_t b200ocl_net_train_workspace_bytes(const b200ocl_net_desc* desc, int N);
 int b200ocl_net_forward_train(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
                               float* out, void* workspace, size_t workspace_bytes, void* stream);
 
-/* loss.backward() for the forward kept in `workspace`: dout [N,out_dim] -> st->grads
+/* loss.backward() for the forward kept in `workspace` (same x): dout [N,out_dim] -> st->grads
  * (overwritten, or added to when accumulate != 0 -- exp_replay.py:55,77 accumulate two
  * backward passes before one opt.step()). */
-int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* dout, int N,
-                         void* workspace, size_t workspace_bytes, int accumulate, void* stream);
+int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, const float* dout,
+                         int N, void* workspace, size_t workspace_bytes, int accumulate, void* stream);
 
 /* opt.step() of torch.optim.SGD without momentum over every tensor that has a gradient
  * (setup_elements.py:73-75), then refresh `packed`.  With dst != NULL the updated weights go

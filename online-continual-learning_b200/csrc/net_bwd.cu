@@ -1,8 +1,590 @@
-// net_bwd.cu -- backward pass of the Reduced-ResNet18 engine (placeholder until the kernels land).
+// net_bwd.cu -- backward pass of the Reduced-ResNet18 / SupConResNet engine (sm_100a).
+//
+// Replaces loss.backward() through reference models/resnet.py:33-36,90-109,159-165
+// (autograd over cuDNN conv / batch-norm backward, addmm, normalize), as used at
+// agents/exp_replay.py:55,77,86 and agents/scr.py:59.
+//
+// Per BasicBlock, in reverse:  BN2 backward (reduce + apply, ReLU mask folded in) -> weight
+// gradient of conv2 -> data gradient of conv2 -> [shortcut BN/conv backward] -> BN1 backward ->
+// weight gradient of conv1 -> data gradient of conv1 accumulated onto the shortcut gradient.
+// Data gradients reuse the implicit-GEMM kernel of conv.cu (transposed gather, [tap][cout][cin]
+// weights).  Weight gradients are a GEMM over pixels: split over pixel ranges, partials reduced
+// in fixed order by one finalize kernel for all layers (deterministic; no float atomics).
+#include <float.h>
+#include <math.h>
+
 #include "net_ws.cuh"
 
-extern "C" int b200ocl_net_backward(const b200ocl_net_desc*, const b200ocl_net_state*, const float*, int, void*, size_t,
-                                    int, void*) {
-  b200ocl::set_error("b200ocl_net_backward: not built yet");
-  return B200OCL_EUNSUPPORTED;
+namespace b200ocl {
+namespace {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const unsigned int s = static_cast<unsigned int>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
+// ----------------------------------------------------------------------------- BN backward
+struct BnBwdArgs {
+  const float* dA;     // gradient w.r.t. the activated output, NHWC [M][C]
+  const float* amask;  // activated output (ReLU mask: > 0), nullable
+  const float* z;      // raw conv output
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  int M, C;
+  int rows_per_cta;
+  double* part;  // [gridDim.x][C][2]
+  unsigned int* counter;
+  float* dgamma;
+  float* dbeta;
+  int accumulate;
+  float* coef;  // [3][C]: gamma*invstd, mean(g), mean(g*xhat)
+  float* dz;
+  float* gout;  // nullable: masked gradient g (identity-shortcut branch)
+};
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
+  extern __shared__ __align__(16) double sred[];  // [R][C][2]
+  __shared__ bool is_last;
+  const int cols = a.C / 4;
+  const int R = 256 / cols;
+  const int tid = threadIdx.x;
+  const int col = tid % cols, rl = tid / cols;
+  const bool active = rl < R;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const float4 mu = *reinterpret_cast<const float4*>(a.mean + col * 4);
+    const float4 is = *reinterpret_cast<const float4*>(a.invstd + col * 4);
+    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int r1 = min(a.M, r0 + a.rows_per_cta);
+    for (int r = r0 + rl; r < r1; r += R) {
+      const size_t i = (size_t)r * cols + col;
+      float4 g = reinterpret_cast<const float4*>(a.dA)[i];
+      if (a.amask) {
+        const float4 m = reinterpret_cast<const float4*>(a.amask)[i];
+        g.x = m.x > 0.f ? g.x : 0.f;
+        g.y = m.y > 0.f ? g.y : 0.f;
+        g.z = m.z > 0.f ? g.z : 0.f;
+        g.w = m.w > 0.f ? g.w : 0.f;
+      }
+      const float4 zz = reinterpret_cast<const float4*>(a.z)[i];
+      s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
+      q[0] = fmaf(g.x, (zz.x - mu.x) * is.x, q[0]);
+      q[1] = fmaf(g.y, (zz.y - mu.y) * is.y, q[1]);
+      q[2] = fmaf(g.z, (zz.z - mu.z) * is.z, q[2]);
+      q[3] = fmaf(g.w, (zz.w - mu.w) * is.w, q[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sred[((size_t)rl * a.C + col * 4 + j) * 2 + 0] = (double)s[j];
+      sred[((size_t)rl * a.C + col * 4 + j) * 2 + 1] = (double)q[j];
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < a.C; c += 256) {
+    double S = 0.0, Q = 0.0;
+    for (int r = 0; r < R; ++r) {
+      S += sred[((size_t)r * a.C + c) * 2 + 0];
+      Q += sred[((size_t)r * a.C + c) * 2 + 1];
+    }
+    a.part[((size_t)blockIdx.x * a.C + c) * 2 + 0] = S;
+    a.part[((size_t)blockIdx.x * a.C + c) * 2 + 1] = Q;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int groups = 256 / a.C > 0 ? 256 / a.C : 1;
+  // channels beyond 256 do not occur (C <= 160)
+  const int ch = tid % a.C, grp = tid / a.C;
+  double S = 0.0, Q = 0.0;
+  if (grp < groups) {
+    for (unsigned int b = grp; b < gridDim.x; b += groups) {
+      S += __ldcg(a.part + ((size_t)b * a.C + ch) * 2 + 0);
+      Q += __ldcg(a.part + ((size_t)b * a.C + ch) * 2 + 1);
+    }
+    sred[((size_t)grp * a.C + ch) * 2 + 0] = S;
+    sred[((size_t)grp * a.C + ch) * 2 + 1] = Q;
+  }
+  __syncthreads();
+  if (tid < a.C) {
+    double db = 0.0, dg = 0.0;
+    for (int g = 0; g < groups; ++g) {
+      db += sred[((size_t)g * a.C + tid) * 2 + 0];
+      dg += sred[((size_t)g * a.C + tid) * 2 + 1];
+    }
+    if (a.accumulate) {
+      a.dgamma[tid] += (float)dg;
+      a.dbeta[tid] += (float)db;
+    } else {
+      a.dgamma[tid] = (float)dg;
+      a.dbeta[tid] = (float)db;
+    }
+    a.coef[tid] = a.gamma[tid] * a.invstd[tid];
+    a.coef[a.C + tid] = (float)(db / (double)a.M);
+    a.coef[2 * a.C + tid] = (float)(dg / (double)a.M);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
+  const size_t n_vec = (size_t)a.M * a.C / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const int c = (int)((i * 4) % (size_t)a.C);
+    float4 g = reinterpret_cast<const float4*>(a.dA)[i];
+    if (a.amask) {
+      const float4 m = reinterpret_cast<const float4*>(a.amask)[i];
+      g.x = m.x > 0.f ? g.x : 0.f;
+      g.y = m.y > 0.f ? g.y : 0.f;
+      g.z = m.z > 0.f ? g.z : 0.f;
+      g.w = m.w > 0.f ? g.w : 0.f;
+    }
+    const float4 zz = reinterpret_cast<const float4*>(a.z)[i];
+    const float4 mu = *reinterpret_cast<const float4*>(a.mean + c);
+    const float4 is = *reinterpret_cast<const float4*>(a.invstd + c);
+    const float4 k1 = *reinterpret_cast<const float4*>(a.coef + c);
+    const float4 mb = *reinterpret_cast<const float4*>(a.coef + a.C + c);
+    const float4 mg = *reinterpret_cast<const float4*>(a.coef + 2 * a.C + c);
+    float4 d;
+    d.x = k1.x * (g.x - mb.x - (zz.x - mu.x) * is.x * mg.x);
+    d.y = k1.y * (g.y - mb.y - (zz.y - mu.y) * is.y * mg.y);
+    d.z = k1.z * (g.z - mb.z - (zz.z - mu.z) * is.z * mg.z);
+    d.w = k1.w * (g.w - mb.w - (zz.w - mu.w) * is.w * mg.w);
+    reinterpret_cast<float4*>(a.dz)[i] = d;
+    if (a.gout) reinterpret_cast<float4*>(a.gout)[i] = g;
+  }
+}
+
+int launch_bn_bwd(BnBwdArgs a, cudaStream_t stream) {
+  const int cols = a.C / 4;
+  const int R = 256 / cols;
+  const int rows = bn_bwd_rows_per_cta(a.M, a.C, sm_count());
+  a.rows_per_cta = rows;
+  const int grid = (a.M + rows - 1) / rows;
+  const int groups = 256 / a.C > 0 ? 256 / a.C : 1;
+  const int srows = R > groups ? R : groups;
+  const size_t smem = (size_t)srows * a.C * 2 * sizeof(double);
+  bn_bwd_reduce_kernel<<<grid, 256, smem, stream>>>(a);
+  B200OCL_LAUNCHED();
+  size_t blocks = ((size_t)a.M * a.C / 4 + 255) / 256;
+  const size_t cap = (size_t)16 * sm_count();
+  if (blocks > cap) blocks = cap;
+  bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
+
+// ----------------------------------------------------------------------------- weight gradient
+// part[split][k][co] = sum over the split's pixels of  x[pixel shifted by tap(k)][ci(k)] * dz[pixel][co]
+struct WgradArgs {
+  const float* x;   // NHWC [N,Hin,Win,Cin]  block input activation
+  const float* dz;  // NHWC [N,Hout,Wout,Cout]
+  float* part;
+  int N, Hin, Win, Cin, Hout, Wout, Cout, ks, stride, pad, M;
+  int k_total, k4_groups, kw, nw, pix_per_split;
+};
+
+constexpr int WG_MC = 16;  // pixels staged per iteration
+
+__global__ void __launch_bounds__(384) wgrad_kernel(WgradArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int KS = a.kw * 128;  // floats of K staged per pixel
+  const int NS = a.nw * 20;
+  float* sA = smem;                 // [MC][KS]
+  float* sG = sA + WG_MC * KS;      // [MC][NS]
+  int* s_base = reinterpret_cast<int*>(sG + WG_MC * NS);  // [MC]
+  int* s_h0 = s_base + WG_MC;
+  int* s_w0 = s_h0 + WG_MC;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x;
+  const int kwi = warp % a.kw, nwi = warp / a.kw;
+  const int g4_base = blockIdx.x * a.kw * 32;          // first k4-group of this CTA
+  const int co_base = blockIdx.y * NS;                 // first output channel of this CTA
+  const int m_begin = blockIdx.z * a.pix_per_split;
+  const int m_end = min(a.M, m_begin + a.pix_per_split);
+  const int hw_out = a.Hout * a.Wout;
+
+  float acc[4][20];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 20; ++c) acc[i][c] = 0.f;
+
+  for (int m0 = m_begin; m0 < m_end; m0 += WG_MC) {
+    __syncthreads();  // previous chunk consumed
+    if (tid < WG_MC) {
+      const int m = m0 + tid;
+      if (m < m_end) {
+        const int n = m / hw_out, rem = m - n * hw_out;
+        const int ho = rem / a.Wout, wo = rem - ho * a.Wout;
+        s_base[tid] = n * a.Hin * a.Win;
+        s_h0[tid] = ho * a.stride - a.pad;
+        s_w0[tid] = wo * a.stride - a.pad;
+      } else {
+        s_base[tid] = 0;
+        s_h0[tid] = -(1 << 20);
+        s_w0[tid] = -(1 << 20);
+      }
+    }
+    __syncthreads();
+    // im2col gather: [MC pixels][kw*32 k4-groups] x 16 bytes
+    for (int idx = tid; idx < WG_MC * a.kw * 32; idx += nthreads) {
+      const int pm = idx / (a.kw * 32), gl = idx - pm * (a.kw * 32);
+      const int g4 = g4_base + gl;
+      bool ok = g4 < a.k4_groups;
+      const float* src = a.x;
+      if (ok) {
+        const int k = g4 * 4;
+        const int tap = k / a.Cin, ci = k - tap * a.Cin;
+        const int kh = tap / a.ks, kwd = tap - kh * a.ks;
+        const int hi = s_h0[pm] + kh, wi = s_w0[pm] + kwd;
+        ok = (unsigned)hi < (unsigned)a.Hin && (unsigned)wi < (unsigned)a.Win;
+        if (ok) src = a.x + ((size_t)(s_base[pm] + hi * a.Win + wi) * a.Cin + ci);
+      }
+      cp_async16(sA + pm * KS + gl * 4, src, ok ? 16 : 0);
+    }
+    for (int idx = tid; idx < WG_MC * (NS / 4); idx += nthreads) {
+      const int pm = idx / (NS / 4), q = idx - pm * (NS / 4);
+      const int m = m0 + pm;
+      const bool ok = (m < m_end) && (co_base + q * 4 < a.Cout);
+      const float* src = ok ? a.dz + (size_t)m * a.Cout + co_base + q * 4 : a.dz;
+      cp_async16(sG + pm * NS + q * 4, src, ok ? 16 : 0);
+    }
+    cp_async_commit_wait_all();
+    __syncthreads();
+    const float* pA = sA + kwi * 128 + lane * 4;
+    const float* pG = sG + nwi * 20;
+#pragma unroll 4
+    for (int pm = 0; pm < WG_MC; ++pm) {
+      const float4 a4 = *reinterpret_cast<const float4*>(pA + pm * KS);
+      float g[20];
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        *reinterpret_cast<float4*>(&g[4 * j]) = *reinterpret_cast<const float4*>(pG + pm * NS + 4 * j);
+#pragma unroll
+      for (int c = 0; c < 20; ++c) {
+        acc[0][c] = fmaf(a4.x, g[c], acc[0][c]);
+        acc[1][c] = fmaf(a4.y, g[c], acc[1][c]);
+        acc[2][c] = fmaf(a4.z, g[c], acc[2][c]);
+        acc[3][c] = fmaf(a4.w, g[c], acc[3][c]);
+      }
+    }
+  }
+  const int g4 = g4_base + kwi * 32 + lane;
+  const int co = co_base + nwi * 20;
+  if (g4 < a.k4_groups && co < a.Cout) {
+    float* dst = a.part + ((size_t)blockIdx.z * a.k_total + (size_t)g4 * 4) * a.Cout + co;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        *reinterpret_cast<float4*>(dst + (size_t)i * a.Cout + 4 * j) =
+            make_float4(acc[i][4 * j], acc[i][4 * j + 1], acc[i][4 * j + 2], acc[i][4 * j + 3]);
+  }
+}
+
+// Stem weight gradient: dW[co][ci][kh][kw] over NCHW images; thread per (k, co), CTA per pixel range.
+__global__ void __launch_bounds__(576) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                         float* __restrict__ part, int N, int H, int W, int M,
+                                                         int pix_per_cta) {
+  const int tid = threadIdx.x;
+  const int k = tid / 20, co = tid - k * 20;  // k = tap*3 + ci
+  const bool active = tid < 540;
+  const int tap = k / 3, ci = k - tap * 3;
+  const int kh = tap / 3, kw = tap - kh * 3;
+  const int hw = H * W;
+  const int m0 = blockIdx.x * pix_per_cta, m1 = min(M, m0 + pix_per_cta);
+  float acc = 0.f;
+  if (active) {
+    for (int m = m0; m < m1; ++m) {
+      const int n = m / hw, rem = m - n * hw;
+      const int ho = rem / W, wo = rem - ho * W;
+      const int hi = ho + kh - 1, wi = wo + kw - 1;
+      if ((unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W)
+        acc = fmaf(__ldg(x + ((size_t)(n * 3 + ci) * H + hi) * W + wi), __ldg(dz + (size_t)m * 20 + co), acc);
+    }
+    part[(size_t)blockIdx.x * 540 + k * 20 + co] = acc;
+  }
+}
+
+// One launch reduces the partials of every conv layer and writes OIHW gradients.
+struct WgFinalTable {
+  int n;
+  struct {
+    unsigned long long part_off;
+    unsigned int w_off;
+    int splits, cin, cout, taps;
+  } e[NET_MAX_CONV];
+};
+
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(WgFinalTable t, const float* __restrict__ part,
+                                                             float* __restrict__ grads, int accumulate) {
+  const auto& L = t.e[blockIdx.y];
+  const int K = L.cin * L.taps;
+  const int total = K * L.cout;
+  const float* p = part + L.part_off;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int k = e / L.cout, co = e - k * L.cout;
+    float s = 0.f;
+    for (int sp = 0; sp < L.splits; ++sp) s += p[(size_t)sp * total + e];
+    const int tap = k / L.cin, ci = k - tap * L.cin;
+    float* dst = grads + L.w_off + ((size_t)co * L.cin + ci) * L.taps + tap;
+    if (accumulate) *dst += s; else *dst = s;
+  }
+}
+
+// ----------------------------------------------------------------------------- heads
+// dpre = (dout - y * <y, dout>) / max(||pre||, eps),  y = pre / max(||pre||, eps)
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dout,
+                                                         float* __restrict__ dpre, int N, int d) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= N) return;
+  const float* x = pre + (size_t)n * d;
+  const float* g = dout + (size_t)n * d;
+  float ss = 0.f, dot = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    ss = fmaf(x[i], x[i], ss);
+    dot = fmaf(x[i], g[i], dot);
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  const float ydot = dot * inv;  // <y, dout>
+  for (int i = lane; i < d; i += 32) dpre[(size_t)n * d + i] = (g[i] - x[i] * inv * ydot) * inv;
+}
+
+// dX[n][i] = sum_o dY[n][o] * W[o][i]   (* 1[mask[n][i] > 0])
+__global__ void __launch_bounds__(256) linear_bwd_x_kernel(const float* __restrict__ dY, const float* __restrict__ W,
+                                                           const float* __restrict__ mask, float* __restrict__ dX, int N,
+                                                           int in, int out) {
+  extern __shared__ float sdy[];
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    __syncthreads();
+    for (int o = threadIdx.x; o < out; o += blockDim.x) sdy[o] = dY[(size_t)n * out + o];
+    __syncthreads();
+    for (int i = threadIdx.x; i < in; i += blockDim.x) {
+      float s = 0.f;
+      for (int o = 0; o < out; ++o) s = fmaf(sdy[o], W[(size_t)o * in + i], s);
+      if (mask && !(mask[(size_t)n * in + i] > 0.f)) s = 0.f;
+      dX[(size_t)n * in + i] = s;
+    }
+  }
+}
+
+// dW[o][i] (+)= sum_n dY[n][o] * X[n][i];  db[o] (+)= sum_n dY[n][o]
+__global__ void __launch_bounds__(256) linear_bwd_w_kernel(const float* __restrict__ dY, const float* __restrict__ X,
+                                                           float* __restrict__ dW, float* __restrict__ db, int N, int in,
+                                                           int out, int accumulate) {
+  const int total = out * in;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int o = e / in, i = e - o * in;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(dY[(size_t)n * out + o], X[(size_t)n * in + i], s);
+    if (accumulate) dW[e] += s; else dW[e] = s;
+    if (i == 0) {
+      float b = 0.f;
+      for (int n = 0; n < N; ++n) b += dY[(size_t)n * out + o];
+      if (accumulate) db[o] += b; else db[o] = b;
+    }
+  }
+}
+
+// gradient of avg_pool2d(., 4) + NCHW flatten:  dA[n,h,w,c] = dfeat[n][(c*PH + h/4)*PW + w/4] / 16
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ dfeat, float* __restrict__ dA, int N,
+                                                       int H, int W, int C, int PH, int PW) {
+  const size_t total = (size_t)N * H * W * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t t = i / C;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H), n = (int)(t / H);
+    float v = 0.f;
+    if (h < 4 * PH && w < 4 * PW) v = dfeat[(size_t)n * (C * PH * PW) + (c * PH + h / 4) * PW + w / 4] * 0.0625f;
+    dA[i] = v;
+  }
+}
+
+int linear_backward(const LinL& l, const float* params, float* grads, const float* X, const float* dY, const float* mask,
+                    float* dX, int N, int accumulate, cudaStream_t stream) {
+  int blocks = (l.in * l.out + 255) / 256;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  linear_bwd_w_kernel<<<blocks, 256, 0, stream>>>(dY, X, grads + l.w_off, grads + l.b_off, N, l.in, l.out, accumulate);
+  B200OCL_LAUNCHED();
+  if (dX) {
+    linear_bwd_x_kernel<<<N < 2 * sm_count() ? N : 2 * sm_count(), 256, l.out * sizeof(float), stream>>>(
+        dY, params + l.w_off, mask, dX, N, l.in, l.out);
+    B200OCL_LAUNCHED();
+  }
+  return B200OCL_OK;
+}
+
+}  // namespace
+}  // namespace b200ocl
+
+extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x,
+                                    const float* dout, int N, void* workspace, size_t workspace_bytes, int accumulate,
+                                    void* stream_) {
+  using namespace b200ocl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200OCL_CHECK_ARG(desc && st && st->params && st->grads && st->packed, "null descriptor/state pointer");
+  NetPlan p;
+  int rc = build_plan(*desc, p);
+  if (rc) {
+    set_error("b200ocl_net_backward: unsupported network description");
+    return rc;
+  }
+  B200OCL_CHECK_ARG(N >= 1 && dout && x, "need N >= 1, x and dout");
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) ||
+      workspace_bytes < b200ocl_net_train_workspace_bytes(desc, N)) {
+    set_error("b200ocl_net_backward: workspace missing, misaligned or too small");
+    return B200OCL_EWORKSPACE;
+  }
+  const int sms = sm_count();
+  TrainWs w = train_ws(p, N, workspace, sms);
+  unsigned int* counters = w.counters + NET_COUNTERS / 2;
+  B200OCL_CUDA(cudaMemsetAsync(counters, 0, (NET_COUNTERS / 2) * sizeof(unsigned int), stream));
+  float* coef = reinterpret_cast<float*>(w.stat_part);                       // [3][C] at the front
+  double* bn_part = w.stat_part + NET_COEF_DOUBLES;                           // partial sums behind the coefficients
+  const int C_last = desc->nf * 8;
+
+  // ---- heads: dout -> dfeat
+  if (p.head == 0) {
+    if ((rc = linear_backward(p.lin[0], st->params, st->grads, w.feat, dout, nullptr, w.dfeat, N, accumulate, stream))) return rc;
+  } else {
+    const float* pre = (p.head == 3) ? w.feat : w.proj;
+    float* dpre = (p.head == 3) ? w.dfeat : w.dproj;
+    l2norm_bwd_kernel<<<(N + 7) / 8, 256, 0, stream>>>(pre, dout, dpre, N, p.out_dim);
+    B200OCL_LAUNCHED();
+    if (p.head == 1) {
+      if ((rc = linear_backward(p.lin[1], st->params, st->grads, w.feat, w.dproj, nullptr, w.dfeat, N, accumulate, stream))) return rc;
+    } else if (p.head == 2) {
+      if ((rc = linear_backward(p.lin[2], st->params, st->grads, w.hid, w.dproj, w.hid, w.dhid, N, accumulate, stream))) return rc;
+      if ((rc = linear_backward(p.lin[1], st->params, st->grads, w.feat, w.dhid, nullptr, w.dfeat, N, accumulate, stream))) return rc;
+    }
+  }
+  float* g0 = w.g0;
+  float* g1 = w.g1;
+  {
+    const size_t total = (size_t)N * p.final_h * p.final_w * C_last;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > (size_t)16 * sms) blocks = (size_t)16 * sms;
+    pool_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w.dfeat, g0, N, p.final_h, p.final_w, C_last, p.pooled_h,
+                                                          p.pooled_w);
+    B200OCL_LAUNCHED();
+  }
+
+  auto bn_backward = [&](int ci, const float* dA, const float* amask, float* dz, float* gout) -> int {
+    const ConvL& c = p.conv[ci];
+    const BnL& b = p.bn[ci];
+    BnBwdArgs a{};
+    a.dA = dA;
+    a.amask = amask;
+    a.z = w.z + (size_t)N * c.act_off;
+    a.mean = w.save + b.save_off;
+    a.invstd = w.save + b.save_off + b.c;
+    a.gamma = st->params + b.g_off;
+    a.M = N * c.hout * c.wout;
+    a.C = c.cout;
+    a.part = bn_part;
+    a.counter = counters + ci;
+    a.dgamma = st->grads + b.g_off;
+    a.dbeta = st->grads + b.b_off;
+    a.accumulate = accumulate;
+    a.coef = coef;
+    a.dz = dz;
+    a.gout = gout;
+    return launch_bn_bwd(a, stream);
+  };
+  auto wgrad = [&](int ci, const float* x, const float* dz) -> int {
+    const ConvL& c = p.conv[ci];
+    const WgradCfg g = wgrad_cfg(c, N, sms);
+    WgradArgs a{};
+    a.x = x; a.dz = dz;
+    a.part = w.wg_part + w.wg_off[ci];
+    a.N = N; a.Hin = c.hin; a.Win = c.win; a.Cin = c.cin;
+    a.Hout = c.hout; a.Wout = c.wout; a.Cout = c.cout;
+    a.ks = c.ks; a.stride = c.stride; a.pad = c.pad;
+    a.M = N * c.hout * c.wout;
+    a.k_total = g.k_total; a.k4_groups = g.k4_groups; a.kw = g.kw; a.nw = g.nw;
+    a.pix_per_split = g.pix_per_split;
+    const size_t smem = (size_t)WG_MC * (g.kw * 128 + g.nw * 20) * sizeof(float) + 3 * WG_MC * sizeof(int);
+    static bool configured = false;
+    if (!configured) {
+      B200OCL_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      configured = true;
+    }
+    wgrad_kernel<<<dim3(g.grid_k, g.grid_n, g.splits), 32 * g.kw * g.nw, smem, stream>>>(a);
+    B200OCL_LAUNCHED();
+    return B200OCL_OK;
+  };
+  auto dgrad = [&](int ci, const float* dz, float* dx, int accum) -> int {
+    const ConvL& c = p.conv[ci];
+    ConvArgs a{};
+    a.in = dz;
+    a.w = st->packed + c.pkd_off;
+    a.out = dx;
+    a.N = N;
+    a.Hin = c.hout; a.Win = c.wout; a.CK = c.cout;
+    a.Hout = c.hin; a.Wout = c.win; a.CN = c.cin;
+    a.ks = c.ks; a.stride = c.stride; a.pad = c.pad;
+    a.transposed = 1;
+    a.M = N * c.hin * c.win;
+    a.mode = accum ? CONV_ACCUM : CONV_RAW;
+    return launch_conv(a, stream);
+  };
+
+  for (int b = 7; b >= 0; --b) {
+    const BlockL& B = p.blk[b];
+    const int prev = (b == 0) ? 0 : p.blk[b - 1].c2;
+    const float* x_in = w.a + (size_t)N * p.conv[prev].act_off;
+    const float* out_act = w.a + (size_t)N * p.conv[B.c2].act_off;
+    const float* a1 = w.a + (size_t)N * p.conv[B.c1].act_off;
+    // main branch, second conv
+    if ((rc = bn_backward(B.c2, g0, out_act, w.g2, B.sc < 0 ? g1 : nullptr))) return rc;
+    if ((rc = wgrad(B.c2, a1, w.g2))) return rc;
+    if ((rc = dgrad(B.c2, w.g2, w.g3, 0))) return rc;
+    // shortcut branch
+    if (B.sc >= 0) {
+      if ((rc = bn_backward(B.sc, g0, out_act, w.g2, nullptr))) return rc;
+      if ((rc = wgrad(B.sc, x_in, w.g2))) return rc;
+      if ((rc = dgrad(B.sc, w.g2, g1, 0))) return rc;
+    }
+    // main branch, first conv
+    if ((rc = bn_backward(B.c1, w.g3, a1, w.g2, nullptr))) return rc;
+    if ((rc = wgrad(B.c1, x_in, w.g2))) return rc;
+    if ((rc = dgrad(B.c1, w.g2, g1, 1))) return rc;
+    float* t = g0; g0 = g1; g1 = t;
+  }
+  // stem
+  if ((rc = bn_backward(0, g0, w.a + (size_t)N * p.conv[0].act_off, w.g2, nullptr))) return rc;
+  {
+    const int M = N * p.in_h * p.in_w;
+    const int ctas = 2 * sms;
+    const int ppc = (M + ctas - 1) / ctas;
+    const int grid = (M + ppc - 1) / ppc;
+    stem_wgrad_kernel<<<grid, 576, 0, stream>>>(x, w.g2, w.wg_part + w.wg_off[0], N, p.in_h, p.in_w, M, ppc);
+    B200OCL_LAUNCHED();
+    WgFinalTable t{};
+    t.n = p.n_conv;
+    for (int i = 0; i < p.n_conv; ++i) {
+      t.e[i].part_off = w.wg_off[i];
+      t.e[i].w_off = (unsigned)p.conv[i].w_off;
+      t.e[i].cin = p.conv[i].cin;
+      t.e[i].cout = p.conv[i].cout;
+      t.e[i].taps = p.conv[i].ks * p.conv[i].ks;
+      t.e[i].splits = (i == 0) ? grid : wgrad_cfg(p.conv[i], N, sms).splits;
+    }
+    wgrad_finalize_kernel<<<dim3(32, p.n_conv), 256, 0, stream>>>(t, w.wg_part, st->grads, accumulate);
+    B200OCL_LAUNCHED();
+  }
+  return B200OCL_OK;
 }

@@ -53,6 +53,15 @@ inline WgradCfg wgrad_cfg(const ConvL& c, int N, int sms) {
   return g;
 }
 
+// Grid of the BN-backward reduction over M pixels x C channels (shared by sizing and launch).
+inline int bn_bwd_rows_per_cta(int M, int C, int sms) {
+  const int R = 256 / (C / 4);
+  int rows = (M + 4 * sms - 1) / (4 * sms);
+  if (rows < 4 * R) rows = 4 * R;
+  return (rows + R - 1) / R * R;
+}
+constexpr int NET_COEF_DOUBLES = 512;  // 3 x 160 floats of BN-backward coefficients fit in front of the partials
+
 struct TrainWs {
   unsigned int* counters;  // NET_COUNTERS x u32 (8 per conv), zeroed at the start of forward / backward
   double* stat_part;
@@ -89,6 +98,9 @@ inline TrainWs train_ws(const NetPlan& p, int N, void* base, int sms) {
     const size_t M = (size_t)N * p.conv[i].hout * p.conv[i].wout;
     const size_t s = (size_t)conv_max_grid_m((int)M) * p.conv[i].cout * 2 * sizeof(double);
     if (s > stat_max) stat_max = s;
+    const int rows = bn_bwd_rows_per_cta((int)M, p.conv[i].cout, sms);
+    const size_t sb = ((M + rows - 1) / rows * p.conv[i].cout * 2 + NET_COEF_DOUBLES) * sizeof(double);
+    if (sb > stat_max) stat_max = sb;
   }
   w.stat_part = reinterpret_cast<double*>(take(stat_max));
   w.save = reinterpret_cast<float*>(take(2 * p.n_bn_channels * sizeof(float)));

@@ -181,12 +181,17 @@ class Engine:
         _native.check(rc, 'b200ocl_net_forward_train')
         return out, ws
 
-    def backward(self, dout, ws, accumulate=False):
+    def backward(self, x, dout, ws, accumulate=False):
+        """loss.backward() for the forward of the same x kept in ws; fills (or adds to) the grad arena."""
         _need_cuda(dout)
+        x = self._x(x)
         dout = dout.detach().to(torch.float32).contiguous()
         n = dout.shape[0]
-        rc = _lib().b200ocl_net_backward(ctypes.byref(self.desc), ctypes.byref(self.state.c), dout.data_ptr(), n,
-                                         ws.data_ptr(), ws.numel(), 1 if accumulate else 0, _stream())
+        if x.shape[0] != n or dout.shape[1] != self.out_dim:
+            raise ValueError('dout must be [N, out_dim] for the same N as x')
+        rc = _lib().b200ocl_net_backward(ctypes.byref(self.desc), ctypes.byref(self.state.c), x.data_ptr(),
+                                         dout.data_ptr(), n, ws.data_ptr(), ws.numel(), 1 if accumulate else 0,
+                                         _stream())
         _native.check(rc, 'b200ocl_net_backward')
 
     def sgd_step(self, lr, weight_decay=0.0, dst=None):

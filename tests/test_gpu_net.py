@@ -50,9 +50,6 @@ def test_eval_features_golden(eng_mod, golden_dir):
     feat = eng.features_eval(torch.tensor(g['mini_x']).cuda()).cpu().numpy()
     assert feat.shape == (2, 640)
     assert rel_err(feat, g['mini_feat_eval']) < 2e-5
-    eng, params, bn = make_engine(eng_mod, oresnet.Spec(32, 20, 100, head='mlp'), 13)
-    feat = eng.features_eval(torch.tensor(g['scr_x1']).cuda()).cpu().numpy()
-    assert rel_err(feat, g['scr_enc_feat_eval']) < 2e-5
 
 
 @pytest.mark.parametrize('N', [1, 10, 37, 110, 270])
@@ -108,6 +105,9 @@ def test_forward_train_mini_and_supcon(eng_mod, golden_dir):
     rm, rv = eng.bn_views()[0]
     assert rel_err(rm.cpu().numpy(), g['scr_rm__encoder.bn1']) < 1e-5
     assert rel_err(rv.cpu().numpy(), g['scr_rv__encoder.bn1']) < 1e-5
+    # eval-mode encoder features AFTER the two train-mode forwards moved the running statistics
+    feat = eng.features_eval(torch.tensor(g['scr_x1']).cuda()).cpu().numpy()
+    assert rel_err(feat, g['scr_enc_feat_eval']) < 2e-5
 
 
 @pytest.mark.parametrize('N', [2, 20, 50, 220])
@@ -150,3 +150,109 @@ def test_sgd_step_and_pack(eng_mod):
     assert rel_err(got, ref) < 2e-5
     flat = torch.cat([v.reshape(-1) for v in params.values()])
     assert rel_err(eng.state.params.cpu().numpy(), flat.numpy()) < 1e-6
+
+
+def _flat_grads(spec, grads):
+    out = []
+    for k, shape in oresnet.param_shapes(spec).items():
+        g = grads.get(k)
+        out.append(torch.zeros(shape).reshape(-1) if g is None else g.reshape(-1))
+    return torch.cat(out)
+
+
+def check_grads(eng, spec, ref_grads, tol=1e-3):
+    """Per-tensor relative error (max |diff| / max |ref|) over every parameter tensor."""
+    worst = 0.0
+    for (name, shape), gv in zip(oresnet.param_shapes(spec).items(), eng.grad_views()):
+        ref = ref_grads.get(name)
+        if ref is None:
+            continue
+        e = rel_err(gv.cpu().numpy().reshape(shape), ref.numpy())
+        assert e < tol, (name, e)
+        worst = max(worst, e)
+    return worst
+
+
+@pytest.mark.parametrize('N', [6, 20])
+def test_backward_ce_cifar(eng_mod, golden_dir, N):
+    spec = oresnet.Spec(32, 20, 100)
+    eng, params, bn = make_engine(eng_mod, spec, 11)
+    if N == 6:
+        g = np.load(os.path.join(golden_dir, 'resnet.npz'))
+        x, y = torch.tensor(g['cifar_x']), torch.tensor(g['cifar_y'])
+    else:
+        gen = torch.Generator().manual_seed(N)
+        x, y = torch.rand(N, 3, 32, 32, generator=gen), torch.randint(0, 100, (N,), generator=gen)
+    loss, logits, ref_grads = oresnet.ce_loss_and_grads(spec, params, bn, x, y)
+    xc = x.cuda()
+    out, ws = eng.forward_train(xc)
+    ce = eng_mod.ce_loss(out, y.cuda())
+    eng.backward(xc, ce['dlogits'], ws)
+    check_grads(eng, spec, ref_grads)
+    if N == 6:   # the reference's own gradients (norms of all 62 tensors + selected tensors)
+        names = [str(n) for n in g['cifar_grad_names']]
+        for n_, ref_norm, gv in zip(names, g['cifar_grad_norms'], eng.grad_views()):
+            assert abs(float(gv.double().norm()) - ref_norm) <= 1e-3 * max(ref_norm, 1e-6), n_
+    # accumulate: a second backward of the same batch doubles the gradient (exp_replay.py:55,77)
+    first = eng.state.grads.clone()
+    eng.backward(xc, ce['dlogits'], ws, accumulate=True)
+    torch.testing.assert_close(eng.state.grads, 2 * first, rtol=1e-5, atol=1e-7)
+
+
+def test_backward_ce_mini(eng_mod, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'resnet.npz'))
+    spec = oresnet.Spec(84, 20, 100)
+    eng, params, bn = make_engine(eng_mod, spec, 12)
+    x, y = torch.tensor(g['mini_x']), torch.tensor(g['mini_y'])
+    loss, logits, ref_grads = oresnet.ce_loss_and_grads(spec, params, bn, x, y)
+    out, ws = eng.forward_train(x.cuda())
+    ce = eng_mod.ce_loss(out, y.cuda())
+    eng.backward(x.cuda(), ce['dlogits'], ws)
+    check_grads(eng, spec, ref_grads)
+
+
+def test_backward_supcon_two_views(eng_mod, golden_dir):
+    """SCR step gradient: two train-mode forwards, fused SupCon loss, two backward passes (scr.py:52-60)."""
+    from b200ocl import ops
+    g = np.load(os.path.join(golden_dir, 'resnet.npz'))
+    spec = oresnet.Spec(32, 20, 100, head='mlp')
+    eng, params, bn = make_engine(eng_mod, spec, 13)
+    x1, x2, y = torch.tensor(g['scr_x1']).cuda(), torch.tensor(g['scr_x2']).cuda(), torch.tensor(g['scr_y']).cuda()
+    f1, ws1 = eng.forward_train(x1, slot=0)
+    f2, ws2 = eng.forward_train(x2, slot=1)
+    feats = torch.stack([f1, f2], dim=1).contiguous()
+    loss, dfeat = ops.supcon(feats, y, 0.07)
+    assert abs(float(loss) - float(g['scr_loss'])) < 1e-4 * abs(float(g['scr_loss']))
+    eng.backward(x1, dfeat[:, 0].contiguous(), ws1)
+    eng.backward(x2, dfeat[:, 1].contiguous(), ws2, accumulate=True)
+    names = [str(n) for n in g['scr_grad_names']]
+    for n_, ref_norm, gv, (_, _, has_grad) in zip(names, g['scr_grad_norms'], eng.grad_views(), eng.table):
+        if has_grad:
+            assert abs(float(gv.double().norm()) - ref_norm) <= 2e-3 * max(ref_norm, 1e-6), (n_, float(gv.norm()), ref_norm)
+    for key in g.files:
+        if key.startswith('scr_grad__'):
+            n_ = key[len('scr_grad__'):]
+            got = eng.grad_views()[names.index(n_)].cpu().numpy()
+            ref = g[key]
+            if got.size > 30000:
+                got = got.reshape(ref.shape[0] if ref.ndim > 1 else -1, -1)[:8] if False else got.reshape(-1, ref.shape[-1])[:8]
+            assert rel_err(got.reshape(ref.shape), ref) < 2e-3, n_
+
+
+def test_train_step_matches_oracle(eng_mod):
+    """forward -> CE -> backward -> SGD, three steps, against the oracle trajectory."""
+    spec = oresnet.Spec(32, 20, 10)
+    eng, params, bn = make_engine(eng_mod, spec, 51)
+    gen = torch.Generator().manual_seed(9)
+    for step in range(3):
+        x, y = torch.rand(20, 3, 32, 32, generator=gen), torch.randint(0, 10, (20,), generator=gen)
+        loss, logits, grads = oresnet.ce_loss_and_grads(spec, params, bn, x, y)
+        oresnet.sgd_step(params, grads, 0.1)
+        out, ws = eng.forward_train(x.cuda())
+        ce = eng_mod.ce_loss(out, y.cuda())
+        # lr 0.1 on a random-init net amplifies fp32 rounding differences step over step
+        assert abs(float(ce['loss']) - float(loss)) < 2e-4 * (4 ** step) * abs(float(loss)), step
+        eng.backward(x.cuda(), ce['dlogits'], ws)
+        eng.sgd_step(0.1)
+    flat = torch.cat([v.reshape(-1) for v in params.values()])
+    assert rel_err(eng.state.params.cpu().numpy(), flat.numpy()) < 1e-2
