@@ -164,6 +164,15 @@ int b200ocl_net_sgd_step(const b200ocl_net_desc* desc, const b200ocl_net_state* 
 int b200ocl_ce_loss(const float* logits, const int64_t* labels, int N, int C, float* loss, float* per_sample,
                     float* dlogits, int64_t* n_correct, void* stream);
 
+/* ---------------------------------------------------------------- SCR augmentation
+ * The second view of agents/scr.py:18-24,54 (kornia RandomResizedCrop -> RandomHorizontalFlip ->
+ * ColorJitter -> RandomGrayscale) in one kernel over NCHW fp32 images in [0,1].
+ * params [N,12] f32 (device), per sample: x0, y0, crop_w, crop_h, flip, jitter_on,
+ * brightness delta, contrast factor, saturation factor, hue shift in turns, order code
+ * (four 2-bit ids, 0 brightness 1 contrast 2 saturation 3 hue, first op in the low bits), gray.
+ * The random draws are the caller's; kornia's exact arithmetic is parity-unpinned (absent). */
+int b200ocl_scr_augment(const float* x, float* out, const float* params, int N, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,3 +7,9 @@ in include/b200ocl.h (libb200ocl.so, loaded with ctypes).  There is no CPU or
 library fallback: every op raises if the CUDA library is missing.
 """
 __version__ = '0.1.0'
+
+
+def install(reference_name_match=None):
+    """Patch the reference registries in place (see registry.install)."""
+    from . import registry
+    return registry.install(reference_name_match)

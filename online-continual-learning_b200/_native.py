@@ -32,6 +32,7 @@ SIGNATURES = {
     'b200ocl_net_backward': (c_int, [P, P, P, P, c_int, P, c_size_t, c_int, P]),
     'b200ocl_net_sgd_step': (c_int, [P, P, c_float, c_float, P, P]),
     'b200ocl_ce_loss': (c_int, [P, P, c_int, c_int, P, P, P, P, P]),
+    'b200ocl_scr_augment': (c_int, [P, P, P, c_int, c_int, c_int, P]),
 }
 
 _lib = None

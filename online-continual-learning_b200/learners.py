@@ -1,0 +1,282 @@
+"""Agents of the replay path with the reference surface `cls(model, opt, params)`,
+`.train_learner(x_train, y_train)`, `.evaluate(test_loaders)`:
+ExperienceReplay (agents/exp_replay.py:10-104: ER / MIR / ASER) and SupContrastReplay
+(agents/scr.py:11-69), over ContinualLearner (agents/base.py:14-113).
+
+The loop structure, the order of train-mode forwards (they move BN running statistics) and the
+order of buffer operations follow the reference step exactly; what changes is who does the
+arithmetic (the CUDA engine, not autograd) and that dead work is not executed: in the ASER
+branch the reference computes and then discards two backward passes (exp_replay.py:55,77,81) --
+their forwards are kept for the BN side effect, their backwards are skipped.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .augment import SCRTransform
+from .engine import ce_loss
+from .memory import Buffer, input_size_match
+from .nets import adopt, engine_of, EngineModel
+
+
+class AverageMeter(object):
+    """utils/utils.py:25-42, but values may stay on the device until avg() is read."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.sum = 0
+        self.count = 0
+
+    def update(self, val, n):
+        self.sum = self.sum + val * n
+        self.count += n
+
+    def avg(self):
+        if self.count == 0:
+            return 0
+        return float(self.sum) / self.count
+
+
+class StreamFeeder(object):
+    """One task's stream: uint8 NHWC images -> fp32 NCHW in [0,1] on the device (ToTensor,
+    continuum/data_utils.py:38-54), shuffled, batches of `batch`, last partial batch dropped
+    (exp_replay.py:21-23).  The whole task is converted once; batches are views."""
+
+    def __init__(self, x_train, y_train, batch, device):
+        self.batch = batch
+        y = np.asarray(y_train).astype(np.int64)
+        perm = torch.randperm(len(y)).numpy()            # DataLoader(shuffle=True) draws from the torch CPU generator
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x_train)[perm]))
+        if x.dtype == torch.uint8:
+            x = x.to(device).permute(0, 3, 1, 2).to(torch.float32).div_(255.0).contiguous()
+        else:                                             # already float NCHW
+            x = x.to(device=device, dtype=torch.float32).contiguous()
+        self.x = x
+        self.y_host = y[perm]
+        self.y = torch.from_numpy(self.y_host).to(device)
+
+    def __len__(self):
+        return len(self.y_host) // self.batch
+
+    def __iter__(self):
+        b = self.batch
+        for i in range(len(self)):
+            yield self.x[i * b:(i + 1) * b], self.y[i * b:(i + 1) * b], self.y_host[i * b:(i + 1) * b]
+
+
+class ContinualLearner(torch.nn.Module):
+    """Label bookkeeping and loss dispatch of agents/base.py:14-113 for the replay path."""
+
+    def __init__(self, model, opt, params):
+        super().__init__()
+        self.params = params
+        self.model = model
+        self.opt = opt
+        self.data = params.data
+        self.cuda = params.cuda
+        self.epoch = params.epoch
+        self.batch = params.batch
+        self.verbose = params.verbose
+        self.old_labels = []
+        self.new_labels = []
+        self.task_seen = 0
+        self.lbl_inv_map = {}
+        self.class_task_map = {}
+        trick = getattr(params, 'trick', None) or {}
+        unsupported = [k for k in ('labels_trick', 'kd_trick', 'separated_softmax', 'review_trick', 'kd_trick_star')
+                       if trick.get(k)]
+        if unsupported:
+            raise NotImplementedError('tricks %s are outside the replay-path scope (SURVEY section 8f)' % unsupported)
+        if isinstance(model, EngineModel):
+            self.engine = model.engine
+        else:
+            self.engine = adopt(model, input_size_match[params.data][1])
+        self.device = self.engine.device
+
+    def _lr_wd(self):
+        """Step size / weight decay from the optimizer the caller built (run.py:40).  Only plain
+        SGD is implemented (setup_elements.py:73-75, the reference default)."""
+        opt = self.opt
+        if opt is None:
+            return float(self.params.learning_rate), float(getattr(self.params, 'weight_decay', 0.0))
+        if not isinstance(opt, torch.optim.SGD):
+            raise NotImplementedError('the b200ocl engine implements torch.optim.SGD only')
+        g = opt.param_groups[0]
+        if g.get('momentum', 0) or g.get('nesterov', False) or g.get('dampening', 0):
+            raise NotImplementedError('SGD momentum/nesterov are not used by the reference and not implemented')
+        return float(g['lr']), float(g['weight_decay'])
+
+    def before_train(self, x_train, y_train):
+        new_labels = list(set(np.asarray(y_train).tolist()))
+        self.new_labels += new_labels
+        for i, lbl in enumerate(new_labels):
+            self.lbl_inv_map[lbl] = len(self.old_labels) + i
+        for i in new_labels:
+            self.class_task_map[i] = self.task_seen
+
+    def after_train(self):
+        self.old_labels += self.new_labels
+        self.new_labels_zombie = list(self.new_labels)
+        self.new_labels.clear()
+        self.task_seen += 1
+
+    def train_learner(self, x_train, y_train):
+        raise NotImplementedError
+
+    def forward(self, x):
+        return self.model.forward(x)
+
+    # ------------------------------------------------------------------ evaluate (next)
+    def _ncm(self):
+        return (getattr(self.params, 'trick', None) or {}).get('ncm_trick') or self.params.agent in ['ICARL', 'SCR', 'SCP']
+
+    @torch.no_grad()
+    def evaluate(self, test_loaders):
+        """Accuracy per task (agents/base.py:118-227): nearest-class-mean over buffer features for
+        SCR / ncm_trick, arg-max of the classifier otherwise.  Encoder features come from the CUDA
+        engine (one batched pass instead of one image at a time, base.py:125-134); the remaining
+        small tensor algebra is torch.  error_analysis is not implemented."""
+        eng = self.engine
+        acc_array = np.zeros(len(test_loaders))
+        ncm = self._ncm()
+        if ncm:
+            n = self.buffer.current_index
+            feats = torch.cat([eng.features_eval(self.buffer.buffer_img[s:s + 512]) for s in range(0, n, 512)]) \
+                if n else torch.zeros((0, eng.dim_in), device=self.device)
+            feats = feats / feats.norm(dim=1, keepdim=True)
+            labels = self.buffer.buffer_label[:n]
+            means = []
+            for cls in self.old_labels:
+                sel = feats[labels == cls]
+                mu = sel.mean(0) if sel.shape[0] else torch.randn(eng.dim_in, device=self.device)
+                means.append(mu / mu.norm())
+            means = torch.stack(means) if means else torch.zeros((0, eng.dim_in), device=self.device)
+            old = torch.tensor(self.old_labels, device=self.device)
+        else:
+            names = [n for n in ('linear__weight', 'linear__bias')]
+            if isinstance(self.model, EngineModel):
+                W, b = getattr(self.model, names[0]), getattr(self.model, names[1])
+            else:
+                W, b = self.model.linear.weight, self.model.linear.bias
+        for task, loader in enumerate(test_loaders):
+            correct = total = 0
+            for batch_x, batch_y in loader:
+                batch_x, batch_y = batch_x.to(self.device), batch_y.to(self.device)
+                f = eng.features_eval(batch_x)
+                if ncm:
+                    f = f / f.norm(dim=1, keepdim=True)
+                    pred = old[torch.cdist(f, means).argmin(1)]
+                else:
+                    pred = (f @ W.t() + b).argmax(1)
+                correct += int((pred == batch_y).sum())
+                total += batch_y.numel()
+            acc_array[task] = correct / max(total, 1)
+        print(acc_array)
+        return acc_array
+
+
+class ExperienceReplay(ContinualLearner):
+    def __init__(self, model, opt, params):
+        super().__init__(model, opt, params)
+        self.buffer = Buffer(model, params)
+        self.mem_size = params.mem_size
+        self.eps_mem_batch = params.eps_mem_batch
+        self.mem_iters = params.mem_iters
+        self._aser_branch = params.update == 'ASER' or params.retrieve == 'ASER'
+        self._needs_batch_grad = params.retrieve == 'MIR' or not self._aser_branch
+
+    def replay_step(self, batch_x, batch_y, batch_y_host, meters=None):
+        """One iteration of exp_replay.py:34-92."""
+        eng = self.engine
+        lr, wd = self._lr_wd()
+        aser = self._aser_branch
+        for _ in range(self.mem_iters):
+            logits, ws = eng.forward_train(batch_x, slot=0)                         # :40  (BN stats move)
+            ce = ce_loss(logits, batch_y, want_grad=self._needs_batch_grad, want_correct=meters is not None)
+            if meters is not None:
+                meters['acc_batch'].update(ce['n_correct'] / batch_y.size(0), batch_y.size(0))
+                meters['losses_batch'].update(ce['loss'], batch_y.size(0))
+            if self._needs_batch_grad:
+                eng.backward(batch_x, ce['dlogits'], ws)                            # :54-55
+            mem_x, mem_y = self.buffer.retrieve(x=batch_x, y=batch_y)               # :58
+            if mem_x.size(0) > 0:
+                mem_logits, ws_m = eng.forward_train(mem_x, slot=1)                 # :62  (BN stats move)
+                ce_m = ce_loss(mem_logits, mem_y, want_grad=not aser, want_correct=meters is not None)
+                if meters is not None:
+                    meters['losses_mem'].update(ce_m['loss'], mem_y.size(0))
+                    meters['acc_mem'].update(ce_m['n_correct'] / mem_y.size(0), mem_y.size(0))
+                if not aser:
+                    eng.backward(mem_x, ce_m['dlogits'], ws_m, accumulate=True)     # :77 (gradients accumulate)
+            if aser:
+                combined = torch.cat((mem_x, batch_x))                              # :82-83
+                labels = torch.cat((mem_y, batch_y))
+                logits_c, ws_c = eng.forward_train(combined, slot=3)                # :84
+                ce_c = ce_loss(logits_c, labels, want_grad=True)
+                eng.backward(combined, ce_c['dlogits'], ws_c)                       # :86
+                self.last_loss = ce_c['loss']
+            else:
+                self.last_loss = ce['loss']
+            eng.sgd_step(lr, wd)                                                    # :87 / :89
+        self.buffer.update(batch_x, batch_y, y_host=batch_y_host)                   # :92
+
+    def train_learner(self, x_train, y_train):
+        self.before_train(x_train, y_train)
+        stream = StreamFeeder(x_train, y_train, self.batch, self.device)
+        self.model = self.model.train()
+        meters = {k: AverageMeter() for k in ('losses_batch', 'losses_mem', 'acc_batch', 'acc_mem')}
+        for ep in range(self.epoch):
+            for i, (batch_x, batch_y, y_host) in enumerate(stream):
+                self.replay_step(batch_x, batch_y, y_host, meters if self.verbose else None)
+                if i % 100 == 1 and self.verbose:
+                    print('==>>> it: {}, avg. loss: {:.6f}, running train acc: {:.3f}'
+                          .format(i, meters['losses_batch'].avg(), meters['acc_batch'].avg()))
+                    print('==>>> it: {}, mem avg. loss: {:.6f}, running mem acc: {:.3f}'
+                          .format(i, meters['losses_mem'].avg(), meters['acc_mem'].avg()))
+        self.after_train()
+
+
+class SupContrastReplay(ContinualLearner):
+    def __init__(self, model, opt, params):
+        super().__init__(model, opt, params)
+        self.buffer = Buffer(model, params)
+        self.mem_size = params.mem_size
+        self.eps_mem_batch = params.eps_mem_batch
+        self.mem_iters = params.mem_iters
+        hw = input_size_match[params.data]
+        self.transform = SCRTransform(size=(hw[1], hw[2]))        # scr.py:18-24
+
+    def replay_step(self, batch_x, batch_y, batch_y_host, meters=None):
+        """One iteration of scr.py:40-63."""
+        eng = self.engine
+        lr, wd = self._lr_wd()
+        for _ in range(self.mem_iters):
+            mem_x, mem_y = self.buffer.retrieve(x=batch_x, y=batch_y)               # :47
+            if mem_x.size(0) > 0:                                                   # :49 (no training on an empty buffer)
+                combined = torch.cat((mem_x, batch_x))                              # :52-53
+                labels = torch.cat((mem_y, batch_y))
+                combined_aug = self.transform(combined)                             # :54
+                f1, ws1 = eng.forward_train(combined, slot=0)                       # :55 two train-mode forwards
+                f2, ws2 = eng.forward_train(combined_aug, slot=1)
+                feats = torch.stack((f1, f2), dim=1)
+                loss, dfeat = ops.supcon(feats, labels, self.params.temp)           # :56  (base.py:109-111)
+                eng.backward(combined, dfeat[:, 0].contiguous(), ws1)               # :58-59
+                eng.backward(combined_aug, dfeat[:, 1].contiguous(), ws2, accumulate=True)
+                eng.sgd_step(lr, wd)                                                # :60
+                self.last_loss = loss
+                if meters is not None:
+                    meters['losses'].update(loss, batch_y.size(0))
+        self.buffer.update(batch_x, batch_y, y_host=batch_y_host)                   # :63
+
+    def train_learner(self, x_train, y_train):
+        self.before_train(x_train, y_train)
+        stream = StreamFeeder(x_train, y_train, self.batch, self.device)
+        self.model = self.model.train()
+        meters = {'losses': AverageMeter()}
+        for ep in range(self.epoch):
+            for i, (batch_x, batch_y, y_host) in enumerate(stream):
+                self.replay_step(batch_x, batch_y, y_host, meters if self.verbose else None)
+                if i % 100 == 1 and self.verbose:
+                    print('==>>> it: {}, avg. loss: {:.6f}, '.format(i, meters['losses'].avg()))
+        self.after_train()

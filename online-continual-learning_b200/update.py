@@ -1,0 +1,141 @@
+"""Buffer update plugins with the reference surface: Reservoir_update
+(utils/buffer/reservoir_update.py:3-60) and ASER_update (utils/buffer/aser_update.py:9-112)."""
+import numpy as np
+import torch
+
+from . import ops
+from .memory import ClassBalancedRandomSampling, n_classes, to_device_i64, uniform_indices
+from .nets import engine_of
+
+
+def _host_labels(y, kwargs):
+    """Labels of the incoming batch on the host: the learners pass y_host=; anything else pays one
+    device->host copy."""
+    yh = kwargs.get('y_host')
+    if yh is None:
+        yh = y.detach().cpu().numpy()
+    return np.asarray(yh, dtype=np.int64)
+
+
+def reservoir_draws(n, n_seen):
+    """The reference draws float32 uniforms in [0, n_seen) and truncates (reservoir_update.py:35);
+    same call on the CPU generator (the reference draws on x's device)."""
+    return torch.FloatTensor(n).uniform_(0, n_seen).long().numpy()
+
+
+def reservoir_plan(draws, mem_size):
+    """Overwrite map of reservoir sampling: slot -> position in the incoming batch; a slot drawn
+    twice keeps the last writer; slots in first-seen order (dict semantics, reservoir_update.py:53)."""
+    idx_map = {}
+    for i, s in enumerate(np.asarray(draws).tolist()):
+        if s < mem_size:
+            idx_map[int(s)] = i
+    return list(idx_map.keys()), list(idx_map.values())
+
+
+class Reservoir_update(object):
+    def __init__(self, params):
+        super().__init__()
+
+    def update(self, buffer, x, y, **kwargs):
+        y_host = _host_labels(y, kwargs)
+        batch_size = x.size(0)
+        mem = buffer.buffer_img.size(0)
+        place_left = max(0, mem - buffer.current_index)
+        if place_left:
+            offset = min(place_left, batch_size)
+            s, e = buffer.current_index, buffer.current_index + offset
+            buffer.buffer_img[s:e].copy_(x[:offset])
+            buffer.buffer_label[s:e].copy_(y[:offset])
+            buffer.labels_host[s:e] = y_host[:offset]
+            buffer.current_index += offset
+            buffer.n_seen_so_far += offset
+            if offset == batch_size:
+                return list(range(s, e))
+        x, y, y_host = x[place_left:], y[place_left:], y_host[place_left:]
+        draws = reservoir_draws(x.size(0), buffer.n_seen_so_far)
+        buffer.n_seen_so_far += x.size(0)
+        slots, src = reservoir_plan(draws, mem)
+        if not slots:
+            return []
+        src_t = to_device_i64(src, x.device)
+        buffer.write(slots, ops.gather_rows(x, src_t) if x.is_cuda else x[src_t],
+                     ops.gather_rows(y, src_t) if y.is_cuda else y[src_t], y_host[src])
+        return slots
+
+
+def aser_update_partition(order, n_cand_buf, cand_ind):
+    """Replacement sets from the descending SV ranking (aser_update.py:88-102): the first
+    n_cand_buf ranks are kept; current-batch samples among them replace the buffered samples
+    among the rest."""
+    order = np.asarray(order)
+    large, small = order[:n_cand_buf], order[n_cand_buf:]
+    ind_cur = large[large >= n_cand_buf] - n_cand_buf
+    ind_buffer = np.asarray(cand_ind)[small[small < n_cand_buf]]
+    return ind_cur, ind_buffer
+
+
+class ASER_update(object):
+    def __init__(self, params, **kwargs):
+        super().__init__()
+        self.device = 'cuda' if torch.cuda.is_available() else 'cpu'
+        self.k = params.k
+        self.mem_size = params.mem_size
+        self.num_tasks = params.num_tasks
+        self.out_dim = n_classes[params.data]
+        self.n_smp_cls = int(params.n_smp_cls)
+        self.n_total_smp = int(params.n_smp_cls * self.out_dim)
+        self.reservoir_update = Reservoir_update(params)
+        ClassBalancedRandomSampling.reset()
+
+    def update(self, buffer, x, y, **kwargs):
+        y_host = _host_labels(y, kwargs)
+        place_left = self.mem_size - buffer.current_index
+        if place_left:
+            # fill phase: sequential insert + class-cache update (aser_update.py:28-35)
+            n_fit = min(place_left, x.size(0))
+            ind = np.arange(buffer.current_index, buffer.current_index + n_fit)
+            ClassBalancedRandomSampling.update_cache(buffer.buffer_label, self.out_dim, new_y=y_host[:n_fit], ind=ind)
+            self.reservoir_update.update(buffer, x[:n_fit], y[:n_fit], y_host=y_host[:n_fit])
+        if buffer.current_index == self.mem_size:
+            self._update_by_knn_sv(buffer, x[place_left:], y[place_left:], y_host[place_left:])
+
+    def minority_positions(self, cur_y_host):
+        """aser_utils.py:148-157: threshold ~ U(0, 1/num_class) from the CPU torch generator."""
+        threshold = torch.tensor(1).float().uniform_(0, 1 / self.out_dim).item()
+        share = ClassBalancedRandomSampling.class_num_cache.astype(np.float32) / np.float32(self.mem_size)
+        return np.flatnonzero(share[cur_y_host] < np.float32(threshold))
+
+    def _update_by_knn_sv(self, buffer, cur_x, cur_y, cur_y_host):
+        eng = engine_of(buffer.model)
+        CB = ClassBalancedRandomSampling
+        dev = cur_x.device
+        n_cur = cur_x.size(0)
+        minority = self.minority_positions(cur_y_host)
+        eval_ind = CB.sample_indices(self.n_smp_cls)
+        cand_ind = uniform_indices(buffer.current_index, self.n_total_smp, excl_indices=eval_ind)
+        n_eval_buf, n_cand_buf = eval_ind.size, cand_ind.size
+        # one batch [eval_buf | cand_buf | cur]; candidates = [cand_buf | cur] are contiguous rows
+        batch = torch.empty((n_eval_buf + n_cand_buf + n_cur,) + tuple(cur_x.shape[1:]), dtype=torch.float32, device=dev)
+        idx_t = to_device_i64(np.concatenate([eval_ind, cand_ind]), dev)
+        ops.gather_rows(buffer.buffer_img, idx_t, out=batch)
+        batch[n_eval_buf + n_cand_buf:].copy_(cur_x)
+        feats = eng.features_eval(batch)
+        cand_f = feats[n_eval_buf:]
+        cand_y = to_device_i64(np.concatenate([buffer.labels_host[cand_ind], cur_y_host]), dev)
+        if minority.size:
+            rows = np.concatenate([np.arange(n_eval_buf), n_eval_buf + n_cand_buf + minority])
+            eval_f = ops.gather_rows(feats, to_device_i64(rows, dev))
+        else:
+            eval_f = feats[:n_eval_buf]
+        eval_y = to_device_i64(np.concatenate([buffer.labels_host[eval_ind], cur_y_host[minority]]), dev)
+        sv_sum = ops.knn_sv(eval_f, eval_y, cand_f, cand_y, self.k, want_sum=True)['sum']
+        order = ops.rank_desc(sv_sum)                                  # full descending ranking
+        ind_cur, ind_buffer = aser_update_partition(order.cpu().numpy(), n_cand_buf, cand_ind)   # the step's one sync
+        buffer.n_seen_so_far += n_cur
+        if ind_cur.size:
+            y_upt_host = cur_y_host[ind_cur]
+            src_t = to_device_i64(ind_cur, dev)
+            CB.update_cache(buffer.buffer_label, self.out_dim, new_y=y_upt_host, ind=ind_buffer)
+            buffer.write(ind_buffer, ops.gather_rows(cur_x, src_t), ops.gather_rows(cur_y, src_t), y_upt_host)
+        self.last_decision = (ind_cur, ind_buffer)

@@ -182,8 +182,8 @@ def sgd_step(params, grads, lr, weight_decay=0.0):
         if g is None:
             continue
         if weight_decay != 0.0:
-            g = g + weight_decay * params[k]
-        params[k] -= lr * g
+            g = g.add(params[k], alpha=weight_decay)
+        params[k].add_(g, alpha=-lr)      # one rounding, like torch.optim.SGD
 
 
 def mir_scores(spec, params, bn, grads, lr, sub_x, sub_y):

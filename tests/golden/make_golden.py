@@ -357,12 +357,131 @@ def gen_reservoir():
     np.savez_compressed(os.path.join(HERE, 'reservoir.npz'), **out)
 
 
+
+# ----------------------------------------------------------------------------- whole replay steps
+def gen_steps():
+    """Run the reference AGENTS (agents/exp_replay.py, agents/scr.py) for a few minibatches on a tiny
+    synthetic task and record every batch, every random choice and the resulting state, so that
+    oracle/replay_step.py can be replayed decision by decision."""
+    from utils.name_match import agents
+    from utils.setup_elements import setup_opt
+    from utils.buffer import random_retrieve as rr_mod
+    from utils.buffer import buffer_utils as bu
+    out = {}
+    CB = buffer_utils.ClassBalancedRandomSampling
+    cfgs = [('er', 'ER', 'random', 'random', 'cifar10', 10), ('mir', 'ER', 'MIR', 'random', 'cifar10', 10),
+            ('aser', 'ER', 'ASER', 'ASER', 'cifar10', 10), ('scr', 'SCR', 'random', 'random', 'cifar100', 20)]
+    for tag, agent_name, retrieve, update, data, eps in cfgs:
+        seed = {'er': 1, 'mir': 2, 'aser': 3, 'scr': 4}[tag]
+        np.random.seed(seed); torch.manual_seed(seed)
+        ncls = 10 if data == 'cifar10' else 100
+        mem = 40
+        params = SimpleNamespace(
+            data=data, cuda=False, epoch=1, batch=10, verbose=False, mem_size=mem, eps_mem_batch=eps, mem_iters=1,
+            update=update, retrieve=retrieve, agent=agent_name, k=3, aser_type='asvm', n_smp_cls=1.5, num_tasks=5,
+            buffer_tracker=False, optimizer='SGD', learning_rate=0.01, weight_decay=0, temp=0.07, head='mlp',
+            subsample=20, error_analysis=False,
+            trick={'labels_trick': False, 'kd_trick': False, 'separated_softmax': False, 'review_trick': False,
+                   'ncm_trick': False, 'kd_trick_star': False})
+        spec = oresnet.Spec(32, 20, ncls, head='mlp' if agent_name == 'SCR' else None)
+        model = setup_architecture(params)
+        p0, bn0 = oresnet.seeded_state(spec, 100 + seed)
+        sd = dict(p0); sd.update(bn0)
+        model.load_state_dict(sd, strict=True)
+        opt = setup_opt('SGD', model, 0.01, 0)     # lr 0.1 on random pixels is chaotic: 1e-7 -> 1e-1 in 6 steps
+        agent = agents[agent_name](model, opt, params)
+        rs = np.random.RandomState(50 + seed)
+        n_steps = 7
+        x_u8 = rs.randint(0, 256, (10 * n_steps, 32, 32, 3)).astype(np.uint8)
+        y = rs.randint(0, 4, 10 * n_steps).astype(np.int64)     # four classes: matches exist among neighbours
+        rec = {'bx': [], 'by': [], 'ret_idx': [], 'draws': [], 'cbrs': [], 'upd_cand': [], 'thr': [], 'mir_idx': []}
+        # hooks -------------------------------------------------------------
+        orig_update = agent.buffer.update
+        def hook_update(x, y_, **kw):
+            rec['bx'].append((x.numpy() * 255).round().astype(np.uint8)); rec['by'].append(y_.numpy().copy())
+            place_left = max(0, mem - agent.buffer.current_index)
+            n_draw = x.shape[0] - place_left if place_left < x.shape[0] else 0
+            if update == 'random':
+                st = torch.get_rng_state()
+                n_after = agent.buffer.n_seen_so_far + min(place_left, x.shape[0])
+                d = torch.FloatTensor(n_draw).uniform_(0, n_after).long().numpy() if n_draw > 0 else np.zeros(0, np.int64)
+                torch.set_rng_state(st)
+                rec['draws'].append(np.pad(d, (0, 10 - len(d)), constant_values=-1))
+            return orig_update(x, y_, **kw)
+        agent.buffer.update = hook_update
+        orig_rr = bu.random_retrieve
+        def hook_rr(buffer, n, excl=None, return_indices=False):
+            r = orig_rr(buffer, n, excl, return_indices=True)
+            rec['last_rr'] = r[2].numpy().copy()
+            return r if return_indices else r[:2]
+        rr_mod.random_retrieve = lambda buffer, n, *a, **k: _rec_ret(hook_rr(buffer, n, *a, **k), rec, eps)
+        def _rec_ret(r, rec_, eps_):
+            idx = rec_['last_rr']
+            rec_['ret_idx'].append(np.pad(idx, (0, eps_ - len(idx)), constant_values=-1))
+            return r
+        mir_retrieve.random_retrieve = lambda buffer, n, *a, **k: _rec_mir(hook_rr(buffer, n, *a, **k), rec)
+        def _rec_mir(r, rec_):
+            idx = rec_['last_rr']
+            rec_['mir_idx'].append(np.pad(idx, (0, 20 - len(idx)), constant_values=-1))
+            return r
+        aser_retrieve.random_retrieve = lambda buffer, n, *a, **k: _rec_ret(hook_rr(buffer, n, *a, **k), rec, eps)
+        def hook_upd_rr(buffer, n, excl=None, return_indices=False):
+            r = orig_rr(buffer, n, excl, return_indices=True)
+            rec['upd_cand'].append(r[2].numpy().copy())
+            return r
+        aser_update.random_retrieve = hook_upd_rr
+        orig_sample = CB.sample.__func__
+        def rec_sample(cls, bxx, byy, n, excl_indices=None, device='cpu'):
+            r = orig_sample(cls, bxx, byy, n, excl_indices=excl_indices, device=device)
+            rec['cbrs'].append(r[2].numpy().copy())
+            return r
+        CB.sample = classmethod(rec_sample)
+        orig_min = aser_update.add_minority_class_input
+        def rec_min(cx, cy, mem_size, num_class):
+            st = torch.get_rng_state()
+            rec['thr'].append(torch.tensor(1).float().uniform_(0, 1 / num_class).item())
+            torch.set_rng_state(st)
+            return orig_min(cx, cy, mem_size, num_class)
+        aser_update.add_minority_class_input = rec_min
+        # run ---------------------------------------------------------------
+        agent.train_learner(x_u8, y)
+        # unhook
+        rr_mod.random_retrieve = orig_rr; mir_retrieve.random_retrieve = orig_rr
+        aser_retrieve.random_retrieve = orig_rr; aser_update.random_retrieve = orig_rr
+        CB.sample = classmethod(orig_sample); aser_update.add_minority_class_input = orig_min
+        out[tag + '_bx'] = np.stack(rec['bx']); out[tag + '_by'] = np.stack(rec['by'])
+        if rec['ret_idx']:
+            out[tag + '_ret_idx'] = np.stack(rec['ret_idx'])
+        if rec['draws']:
+            out[tag + '_draws'] = np.stack(rec['draws'])
+        if rec['mir_idx']:
+            out[tag + '_mir_idx'] = np.stack(rec['mir_idx'])
+        for j, c in enumerate(rec['cbrs']):
+            out['%s_cbrs%d' % (tag, j)] = c
+        out[tag + '_n_cbrs'] = np.int64(len(rec['cbrs']))
+        for j, c in enumerate(rec['upd_cand']):
+            out['%s_updcand%d' % (tag, j)] = c
+        out[tag + '_n_updcand'] = np.int64(len(rec['upd_cand']))
+        out[tag + '_thr'] = np.array(rec['thr'], dtype=np.float64)
+        out[tag + '_final_labels'] = agent.buffer.buffer_label.numpy().copy()
+        out[tag + '_final_img_sum'] = agent.buffer.buffer_img.numpy().reshape(mem, -1).sum(1)
+        out[tag + '_n_seen'] = np.int64(agent.buffer.n_seen_so_far)
+        names, norms = [], []
+        for name, prm in model.named_parameters():
+            names.append(name); norms.append(float(prm.detach().double().norm()))
+        out[tag + '_param_names'] = np.array(names); out[tag + '_param_norms'] = np.array(norms)
+        out[tag + '_rm_bn1'] = [v for k_, v in model.state_dict().items() if k_.endswith('bn1.running_mean')][0].numpy().copy()
+        out[tag + '_lin_w'] = [prm for n_, prm in model.named_parameters() if n_.endswith('linear.weight') or n_ == 'head.2.weight'][-1].detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, 'steps.npz'), **out)
+
+
 if __name__ == '__main__':
     gen_knn_sv()
     gen_supcon()
     gen_resnet()
     gen_aser()
     gen_reservoir()
+    gen_steps()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))
