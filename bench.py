@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Replay-step throughput bench (BASELINE.json metric: replay-step images/sec, ASER+SCR,
+Reduced-ResNet18, CIFAR-100 shapes, mem_size 5000).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One *step* = one ER+ASER replay step (BASELINE config 3: asvm, k=3, n_smp_cls 1.5, 10 stream + 10
+replayed images) AND one SCR replay step (BASELINE config 2: SupCon temp 0.07, mlp head, 10 stream +
+100 replayed images), each on its own learner with its own pre-filled 5000-slot memory; 20 stream
+images per step.  Inputs are synthetic (uniform images, uniform labels), weights random-init.
+
+  value  stream images/sec with the stream batches already resident in HBM
+  e2e    the same through the public plugin API with HOST batches: pinned host -> device copy of
+         every batch and a device -> host read of both losses inside the timed region
+  N > 1  data-parallel stream shards: every rank runs its own stream shard and memory, gradients are
+         averaged with one NCCL all-reduce of the flat gradient arena per optimizer step (weak scaling)
+  --impl reference   the reference's algorithm on the host CPU cores (oracle/replay_step.py, the
+         restatement pinned against the reference's agents; /root/reference does not travel to the box)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MEM_SIZE = 5000
+BATCH = 10
+NUM_CLASSES = 100
+TRICK = {'labels_trick': False, 'kd_trick': False, 'separated_softmax': False, 'review_trick': False,
+         'ncm_trick': False, 'kd_trick_star': False}
+
+
+def params_for(kind):
+    base = dict(data='cifar100', cuda=True, epoch=1, batch=BATCH, verbose=False, mem_size=MEM_SIZE, mem_iters=1,
+                k=3, aser_type='asvm', n_smp_cls=1.5, num_tasks=10, buffer_tracker=False, optimizer='SGD',
+                learning_rate=0.1, weight_decay=0, temp=0.07, head='mlp', subsample=50, error_analysis=False,
+                trick=dict(TRICK))
+    if kind == 'aser':
+        base.update(agent='ER', retrieve='ASER', update='ASER', eps_mem_batch=10)
+    else:
+        base.update(agent='SCR', retrieve='random', update='random', eps_mem_batch=100)
+    return SimpleNamespace(**base)
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {'hbm_gbs': p['hbm_gbs'], 'bf16_tflops': p['bf16_tflops'],
+                'bf16_tflops_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CUDA arm
+def build_learner(kind, seed):
+    import torch
+    from b200ocl import nets, registry
+    from b200ocl.memory import ClassBalancedRandomSampling as CB
+    p = params_for(kind)
+    model = nets.setup_architecture(p)
+    learner = registry.agents[p.agent](model, None, p)
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    buf = learner.buffer
+    buf.buffer_img.copy_(torch.rand(buf.buffer_img.shape, device='cuda', generator=g))
+    labels = np.random.RandomState(seed).randint(0, NUM_CLASSES, MEM_SIZE).astype(np.int64)
+    buf.buffer_label.copy_(torch.from_numpy(labels).cuda())
+    buf.labels_host[:] = labels
+    buf.current_index = MEM_SIZE
+    buf.n_seen_so_far = MEM_SIZE + BATCH            # > mem_size: ASER retrieval is active (aser_retrieve.py:24)
+    if kind == 'aser':
+        CB.reset()
+        CB.update_cache(buf.buffer_label, NUM_CLASSES, new_y=labels, ind=np.arange(MEM_SIZE))
+    learner.model.train()
+    return learner
+
+
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from b200ocl import _native, ops
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    np.random.seed(1000 + rank)
+    torch.manual_seed(1000 + rank)
+    aser = build_learner('aser', 10 + rank)
+    scr = build_learner('scr', 20 + rank)
+    if world > 1:
+        # same initial weights on every rank, then gradient averaging keeps the replicas identical
+        for L in (aser, scr):
+            dist.broadcast(L.engine.state.params, src=0)
+            dist.broadcast(L.engine.state.bn_stats, src=0)
+            L.engine.pack()
+            L.grad_sync = lambda eng: dist.all_reduce(eng.state.grads)
+            L.grad_world = world
+    total = args.warmup + args.steps
+    rs = np.random.RandomState(7 + rank)
+    host_x = torch.from_numpy(rs.rand(2 * total, BATCH, 3, 32, 32).astype(np.float32)).pin_memory()
+    host_y = rs.randint(0, NUM_CLASSES, (2 * total, BATCH)).astype(np.int64)
+    dev_x = host_x.to(dev)
+    dev_y = torch.from_numpy(host_y).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step(i, from_host):
+        if from_host:
+            xa = host_x[2 * i].to(dev, non_blocking=True); xs = host_x[2 * i + 1].to(dev, non_blocking=True)
+            ya = torch.from_numpy(host_y[2 * i]).pin_memory().to(dev, non_blocking=True)
+            ys = torch.from_numpy(host_y[2 * i + 1]).pin_memory().to(dev, non_blocking=True)
+        else:
+            xa, xs, ya, ys = dev_x[2 * i], dev_x[2 * i + 1], dev_y[2 * i], dev_y[2 * i + 1]
+        aser.replay_step(xa, ya, host_y[2 * i])
+        scr.replay_step(xs, ys, host_y[2 * i + 1])
+        if from_host:
+            return float(aser.last_loss), float(scr.last_loss)       # device -> host read of the step's result
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(from_host):
+        for i in range(args.warmup):
+            step(i, from_host)
+        barrier()
+        launches0 = _native.launch_count()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            flush.fill_(k & 255)                      # L2 flush between timed iterations (outside the event pair)
+            ev[k][0].record()
+            step(args.warmup + k, from_host)
+            ev[k][1].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if rank == 0 else None
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _native.launch_count() - launches0, clocks, wall
+
+    ms_dev, launches, clocks, wall = timed(False)
+    ms_e2e, _, _, _ = timed(True)
+    if rank != 0:
+        return None
+    imgs = 2 * BATCH * world * args.steps
+    # per-kernel-class device time of one step (separate pass, event-bracketed inside the library)
+    prof = profile_step(lambda i: step(i, False), args.warmup + args.steps - 1) if world == 1 else None
+    pk = peaks()
+    line = {
+        'metric': 'replay-step images/sec (ASER+SCR, ResNet18, CIFAR100)', 'value': imgs / (ms_dev * 1e-3),
+        'unit': 'stream images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'ER+ASER replay step (asvm,k=3,n_smp_cls=1.5,10+10 imgs) + SCR replay step '
+                               '(SupCon T=0.07,mlp head,10+100 imgs x 2 views), CIFAR-100 shapes, mem_size 5000, batch 10',
+                   'stream_images_per_step': 2 * BATCH, 'trained_images_per_step': 20 + 110,
+                   'parallelism': 'dp%d stream shards, NCCL grad all-reduce' % world if world > 1 else 'single GPU',
+                   'l2': 'flushed (256 MiB write) between timed steps', 'wall_s_timed_region': wall},
+        'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': 'stream images/s',
+                'h2d_bytes_per_step': 2 * (BATCH * 3 * 32 * 32 * 4 + BATCH * 8), 'd2h_bytes_per_step': 8},
+        'gpu_launches': int(launches), 'clocks': clocks,
+    }
+    if prof is not None:
+        line['roofline'] = prof['roofline']
+        line['kernel_ms_per_step'] = prof['classes']
+    return line
+
+
+def profile_step(step_fn, i):
+    """Device time per kernel class for one step, CUDA events recorded around every launch by the
+    library on its launch stream (b200ocl_profile_*).  Returns the roofline object for the class with
+    the largest share."""
+    import torch
+    from b200ocl import _native
+    lib = _native.lib()
+    if not hasattr(lib, 'b200ocl_profile_begin'):
+        return None
+    torch.cuda.synchronize()
+    lib.b200ocl_profile_begin()
+    step_fn(i)
+    torch.cuda.synchronize()
+    import ctypes
+    n = lib.b200ocl_profile_end()
+    classes = {}
+    name = ctypes.create_string_buffer(64)
+    ms, cnt, work = ctypes.c_double(), ctypes.c_int(), ctypes.c_double()
+    for k in range(n):
+        lib.b200ocl_profile_get(k, name, 64, ctypes.byref(ms), ctypes.byref(cnt), ctypes.byref(work))
+        classes[name.value.decode()] = {'ms': ms.value, 'launches': cnt.value, 'work': work.value}
+    if not classes:
+        return None
+    top = max(classes, key=lambda c: classes[c]['ms'])
+    pk = peaks()
+    c = classes[top]
+    total_ms = sum(v['ms'] for v in classes.values())
+    if top.startswith('conv') or top.startswith('wgrad'):
+        achieved = c['work'] / (c['ms'] * 1e-3) / 1e12 if c['ms'] > 0 else 0.0      # work = FLOPs
+        roof = {'kernel': top, 'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'],
+                'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
+                'peak_source': pk['source'] + ' cuBLAS bf16 (sustained); the kernel computes in fp32 on the CUDA cores',
+                'share_of_step': c['ms'] / total_ms, 'avg_launch_us': 1e3 * c['ms'] / max(c['launches'], 1)}
+    else:
+        achieved = c['work'] / (c['ms'] * 1e-3) / 1e9 if c['ms'] > 0 else 0.0       # work = bytes
+        roof = {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                'frac': achieved / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['source'],
+                'share_of_step': c['ms'] / total_ms, 'avg_launch_us': 1e3 * c['ms'] / max(c['launches'], 1)}
+    return {'roofline': roof, 'classes': {k: round(v['ms'], 4) for k, v in sorted(classes.items(), key=lambda kv: -kv[1]['ms'])}}
+
+
+# ----------------------------------------------------------------------------- CPU arm (reference algorithm)
+def build_oracle_state(kind, seed):
+    import torch
+    from oracle import replay_step as ors
+    from oracle import resnet as oresnet
+    spec = oresnet.Spec(32, 20, NUM_CLASSES, head='mlp' if kind == 'scr' else None)
+    params, bn = oresnet.seeded_state(spec, seed)
+    for name in oresnet.bn_names(spec):           # fresh-model statistics
+        bn[name + '.running_mean'].zero_(); bn[name + '.running_var'].fill_(1.0)
+    st = ors.ReplayState(spec, params, bn, MEM_SIZE, (3, 32, 32), NUM_CLASSES, lr=0.1)
+    rs = np.random.RandomState(seed)
+    st.buffer_img = torch.from_numpy(rs.rand(MEM_SIZE, 3, 32, 32).astype(np.float32))
+    labels = rs.randint(0, NUM_CLASSES, MEM_SIZE).astype(np.int64)
+    st.buffer_label = torch.from_numpy(labels)
+    st.current_index = MEM_SIZE
+    st.n_seen_so_far = MEM_SIZE + BATCH
+    if kind == 'aser':
+        st.cache_update_bulk = True
+        for c in range(NUM_CLASSES):
+            st.class_index_cache[c] = set(np.flatnonzero(labels == c).tolist())
+            st.class_num_cache[c] = len(st.class_index_cache[c])
+    return st
+
+
+def run_reference(args, steps, warmup):
+    """The reference's replay step on the host cores: oracle/replay_step.py (CPU, torch intra-op
+    threads = all cores).  Each step is one ER+ASER step and one SCR step like the CUDA arm."""
+    import torch
+    from oracle import replay_step as ors
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    np.random.seed(0); torch.manual_seed(0)
+    st_a, st_s = build_oracle_state('aser', 31), build_oracle_state('scr', 32)
+    rs = np.random.RandomState(5)
+
+    def step():
+        xa = torch.from_numpy(rs.rand(BATCH, 3, 32, 32).astype(np.float32)); ya = torch.from_numpy(rs.randint(0, NUM_CLASSES, BATCH))
+        xs = torch.from_numpy(rs.rand(BATCH, 3, 32, 32).astype(np.float32)); ys = torch.from_numpy(rs.randint(0, NUM_CLASSES, BATCH))
+        ors.er_step(st_a, xa, ya, retrieve='ASER', update='ASER', eps_mem_batch=10, k=3, aser_type='asvm', n_smp_cls=1)
+        ors.scr_step(st_s, xs, ys, eps_mem_batch=100, temperature=0.07)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {'value': 2 * BATCH * steps / dt, 'unit': 'stream images/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d steps (one ER+ASER + one SCR replay step each) of the same workload after %d warm-up, '
+                      '%.1f s of CPU time, torch intra-op threads = %d' % (steps, warmup, dt, cores),
+            'ms_per_step': 1e3 * dt / steps}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        steps, warmup = min(args.steps, 12), min(args.warmup, 2)
+        r = run_reference(args, steps, warmup)
+        line = {'impl': 'reference', 'metric': 'replay-step images/sec (ASER+SCR, ResNet18, CIFAR100)',
+                'value': r['value'], 'unit': 'stream images/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
+                'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'ER+ASER replay step + SCR replay step, CIFAR-100 shapes, mem_size 5000, batch 10 '
+                                       '(reference algorithm, host CPU)', 'stream_images_per_step': 2 * BATCH},
+                'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+                'e2e': {'value': r['value'], 'unit': 'stream images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0))))
+    line = run_ours(args, rank, world)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            r = run_reference(args, 8, 1)
+            line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

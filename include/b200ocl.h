@@ -41,6 +41,13 @@ const char* b200ocl_last_error(void);
 int b200ocl_version(void);
 /* Number of kernel launches issued through this library since load (bench.py reports it). */
 uint64_t b200ocl_launch_count(void);
+/* Optional per-launch device timing for bench.py's roofline: between begin and end every launch of
+ * this library is bracketed by CUDA events on its launch stream and accumulated per kernel class
+ * together with its algorithmic work (FLOPs for conv/wgrad classes, bytes otherwise).
+ * profile_end synchronises the device and returns the number of classes. */
+void b200ocl_profile_begin(void);
+int b200ocl_profile_end(void);
+int b200ocl_profile_get(int k, char* name, int name_len, double* ms, int* launches, double* work);
 
 /* ---------------------------------------------------------------- kNN Shapley values
  * Replaces compute_knn_sv minus its network forward: sorted_cand_ind +

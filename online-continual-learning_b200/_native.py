@@ -13,6 +13,9 @@ SIGNATURES = {
     'b200ocl_last_error': (c_char_p, []),
     'b200ocl_version': (c_int, []),
     'b200ocl_launch_count': (c_uint64, []),
+    'b200ocl_profile_begin': (None, []),
+    'b200ocl_profile_end': (c_int, []),
+    'b200ocl_profile_get': (c_int, [c_int, P, c_int, P, P, P]),
     'b200ocl_knn_sv_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'b200ocl_knn_sv': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P]),
     'b200ocl_rank_desc': (c_int, [P, c_float, P, c_float, c_int, P, c_int, P, P]),

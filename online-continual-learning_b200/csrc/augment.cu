@@ -114,6 +114,7 @@ extern "C" int b200ocl_scr_augment(const float* x, float* out, const float* para
   const int total = N * H * W;
   int blocks = (total + 255) / 256;
   if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+  B200OCL_PROF("scr_augment", 24.0 * total, stream);
   scr_augment_kernel<<<blocks, 256, 0, stream>>>(x, out, params, N, H, W);
   B200OCL_LAUNCHED();
   return B200OCL_OK;

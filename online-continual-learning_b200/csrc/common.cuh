@@ -10,6 +10,11 @@
 namespace b200ocl {
 
 void set_error(const char* fmt, ...);
+// Optional per-launch timing (bench.py roofline): when enabled, every launch is bracketed by CUDA
+// events on its own stream and accumulated per kernel class.  Off by default (no overhead).
+extern bool g_prof_on;
+void prof_begin(const char* kernel_class, double work, cudaStream_t stream);
+void prof_end();
 extern std::atomic<uint64_t> g_launches;
 int sm_count();
 
@@ -34,8 +39,15 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
   } while (0)
 
 // Count the launch and surface launch-configuration errors immediately.
+// Declare the kernel class and its algorithmic work (FLOPs or bytes) right before a launch.
+#define B200OCL_PROF(kernel_class, work, stream)                                              \
+  do {                                                                                        \
+    if (b200ocl::g_prof_on) b200ocl::prof_begin(kernel_class, (double)(work), stream);        \
+  } while (0)
+
 #define B200OCL_LAUNCHED()                                                                    \
   do {                                                                                        \
+    if (b200ocl::g_prof_on) b200ocl::prof_end();                                              \
     b200ocl::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
     cudaError_t err__ = cudaGetLastError();                                                   \
     if (err__ != cudaSuccess) {                                                               \

@@ -347,6 +347,7 @@ int launch_conv_cfg(const ConvArgs& a, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((a.M + BM - 1) / BM, a.CN / BN);
+  B200OCL_PROF(a.transposed ? "conv_dgrad" : (a.mode == CONV_EVAL ? "conv_eval" : "conv_train"), 2.0 * a.M * (double)a.CN * a.CK * a.ks * a.ks, stream);
   conv_kernel<BN, PT><<<grid, CONV_THREADS, smem, stream>>>(a);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
@@ -398,6 +399,7 @@ int launch_stem(const ConvArgs& a, cudaStream_t stream) {
     set_error("launch_stem: only the 3->20 3x3 stride-1 stem is supported");
     return B200OCL_EUNSUPPORTED;
   }
+  B200OCL_PROF(a.mode == CONV_EVAL ? "conv_eval" : "conv_train", 2.0 * a.M * 20.0 * 27.0, stream);
   stem_kernel<<<(a.M + CONV_THREADS - 1) / CONV_THREADS, CONV_THREADS, 0, stream>>>(a);
   B200OCL_LAUNCHED();
   return B200OCL_OK;

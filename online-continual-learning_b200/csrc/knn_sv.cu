@@ -314,6 +314,7 @@ int launch_knn(const KnnSvParams& p0, cudaStream_t stream) {
     B200OCL_CUDA(cudaFuncSetAttribute(knn_sv_kernel<KPL, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  B200OCL_PROF("knn_sv", 4.0 * p.d * ((double)p.E + p.C) + 8.0 * ((double)p.E + p.C) + 4.0 * p.C * 3 + (p.sv ? 4.0 * p.E * p.C : 0.0), stream);
   knn_sv_kernel<KPL, TE><<<grid, KNN_THREADS, smem, stream>>>(p);
   B200OCL_LAUNCHED();
   return B200OCL_OK;

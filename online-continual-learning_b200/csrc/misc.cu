@@ -71,6 +71,7 @@ int move_rows(const void* src, const int64_t* idx, int n_rows, size_t row_bytes,
   const bool vec16 = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
   const int grid = n_rows < 8 * sm_count() ? n_rows : 8 * sm_count();
+  B200OCL_PROF("move_rows", 2.0 * n_rows * (double)row_bytes, stream);
   if (vec16)
     move_rows_kernel<SCATTER, uint4><<<grid, 256, 0, stream>>>(static_cast<const unsigned char*>(src),
                                                                reinterpret_cast<const long long*>(idx), n_rows,
@@ -114,6 +115,7 @@ int b200ocl_rank_desc(const float* a, float sa, const float* b, float sb, int n,
   int npad = 2;
   while (npad < n) npad <<= 1;
   const int threads = npad / 2 < 32 ? 32 : (npad / 2 > 1024 ? 1024 : npad / 2);
+  B200OCL_PROF("rank_desc", 12.0 * n, stream);
   rank_desc_kernel<<<1, threads, (size_t)npad * sizeof(unsigned long long), stream>>>(
       a, sa, b, sb, n, npad, reinterpret_cast<long long*>(idx_out), n_out, score_out);
   B200OCL_LAUNCHED();
@@ -142,6 +144,7 @@ int b200ocl_sgd_step(const float* p, const float* g, float* out, size_t n, float
   size_t blocks = (n + 255) / 256;
   const size_t cap = (size_t)8 * sm_count();
   if (blocks > cap) blocks = cap;
+  B200OCL_PROF("sgd", 12.0 * n, stream);
   sgd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, g, out, n, lr, wd);
   B200OCL_LAUNCHED();
   return B200OCL_OK;

@@ -170,11 +170,13 @@ int launch_bn_bwd(BnBwdArgs a, cudaStream_t stream) {
   const int groups = 256 / a.C > 0 ? 256 / a.C : 1;
   const int srows = R > groups ? R : groups;
   const size_t smem = (size_t)srows * a.C * 2 * sizeof(double);
+  B200OCL_PROF("bn_bwd", (a.amask ? 12.0 : 8.0) * a.M * a.C, stream);
   bn_bwd_reduce_kernel<<<grid, 256, smem, stream>>>(a);
   B200OCL_LAUNCHED();
   size_t blocks = ((size_t)a.M * a.C / 4 + 255) / 256;
   const size_t cap = (size_t)16 * sm_count();
   if (blocks > cap) blocks = cap;
+  B200OCL_PROF("bn_bwd", (a.amask ? 16.0 : 12.0) * a.M * a.C + (a.gout ? 4.0 * a.M * a.C : 0.0), stream);
   bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
@@ -417,9 +419,11 @@ int linear_backward(const LinL& l, const float* params, float* grads, const floa
                     float* dX, int N, int accumulate, cudaStream_t stream) {
   int blocks = (l.in * l.out + 255) / 256;
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  B200OCL_PROF("head", 4.0 * ((double)N * l.in + (double)N * l.out + (double)l.in * l.out), stream);
   linear_bwd_w_kernel<<<blocks, 256, 0, stream>>>(dY, X, grads + l.w_off, grads + l.b_off, N, l.in, l.out, accumulate);
   B200OCL_LAUNCHED();
   if (dX) {
+    B200OCL_PROF("head", 4.0 * ((double)N * l.in + (double)N * l.out + (double)l.in * l.out), stream);
     linear_bwd_x_kernel<<<N < 2 * sm_count() ? N : 2 * sm_count(), 256, l.out * sizeof(float), stream>>>(
         dY, params + l.w_off, mask, dX, N, l.in, l.out);
     B200OCL_LAUNCHED();
@@ -462,6 +466,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
   } else {
     const float* pre = (p.head == 3) ? w.feat : w.proj;
     float* dpre = (p.head == 3) ? w.dfeat : w.dproj;
+    B200OCL_PROF("head", 12.0 * N * p.out_dim, stream);
     l2norm_bwd_kernel<<<(N + 7) / 8, 256, 0, stream>>>(pre, dout, dpre, N, p.out_dim);
     B200OCL_LAUNCHED();
     if (p.head == 1) {
@@ -477,6 +482,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     const size_t total = (size_t)N * p.final_h * p.final_w * C_last;
     size_t blocks = (total + 255) / 256;
     if (blocks > (size_t)16 * sms) blocks = (size_t)16 * sms;
+    B200OCL_PROF("pool", 8.0 * total, stream);
     pool_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w.dfeat, g0, N, p.final_h, p.final_w, C_last, p.pooled_h,
                                                           p.pooled_w);
     B200OCL_LAUNCHED();
@@ -522,6 +528,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
       B200OCL_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       configured = true;
     }
+    B200OCL_PROF("wgrad", 2.0 * a.M * (double)a.k_total * a.Cout, stream);
     wgrad_kernel<<<dim3(g.grid_k, g.grid_n, g.splits), 32 * g.kw * g.nw, smem, stream>>>(a);
     B200OCL_LAUNCHED();
     return B200OCL_OK;
@@ -571,6 +578,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     const int ctas = 2 * sms;
     const int ppc = (M + ctas - 1) / ctas;
     const int grid = (M + ppc - 1) / ppc;
+    B200OCL_PROF("wgrad", 2.0 * M * 540.0, stream);
     stem_wgrad_kernel<<<grid, 576, 0, stream>>>(x, w.g2, w.wg_part + w.wg_off[0], N, p.in_h, p.in_w, M, ppc);
     B200OCL_LAUNCHED();
     WgFinalTable t{};
@@ -583,6 +591,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
       t.e[i].taps = p.conv[i].ks * p.conv[i].ks;
       t.e[i].splits = (i == 0) ? grid : wgrad_cfg(p.conv[i], N, sms).splits;
     }
+    B200OCL_PROF("wgrad_finalize", 8.0 * p.n_packed / 2, stream);
     wgrad_finalize_kernel<<<dim3(32, p.n_conv), 256, 0, stream>>>(t, w.wg_part, st->grads, accumulate);
     B200OCL_LAUNCHED();
   }

@@ -46,6 +46,7 @@ int launch_pack(const NetPlan& p, const float* params, float* packed, cudaStream
     t.e[i].cout = p.conv[i].cout;
     t.e[i].taps = p.conv[i].ks * p.conv[i].ks;
   }
+  B200OCL_PROF("pack", 12.0 * p.n_packed / 2, stream);
   pack_kernel<<<dim3(16, p.n_conv), 256, 0, stream>>>(t, params, packed);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
@@ -122,6 +123,7 @@ int launch_bn_apply(const BnApplyArgs& a, cudaStream_t stream) {
   size_t blocks = (a.n_vec + 255) / 256;
   const size_t cap = (size_t)16 * sm_count();
   if (blocks > cap) blocks = cap;
+  B200OCL_PROF("bn_apply", (a.res ? 48.0 : 32.0) * a.n_vec, stream);
   bn_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
 int launch_linear_fwd(const float* x, const float* W, const float* b, float* y, int N, int in, int out, int relu,
                       cudaStream_t stream) {
   int gy = N < 32 ? N : 32;
+  B200OCL_PROF("head", 4.0 * ((double)N * in + (double)in * out + (double)N * out), stream);
   linear_fwd_kernel<<<dim3((out + 7) / 8, gy), 256, 0, stream>>>(x, W, b, y, N, in, out, relu);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
@@ -343,6 +346,7 @@ int head_forward(const NetPlan& p, const b200ocl_net_state& st, const float* fea
     if ((rc = launch_linear_fwd(hid, st.params + l2.w_off, st.params + l2.b_off, proj, N, l2.in, l2.out, 0, stream))) return rc;
     pre = proj;
   }
+  B200OCL_PROF("head", 8.0 * N * p.out_dim, stream);
   l2norm_fwd_kernel<<<(N + 7) / 8, 256, 0, stream>>>(pre, out, N, p.out_dim);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
@@ -440,6 +444,7 @@ int b200ocl_net_sgd_step(const b200ocl_net_desc* desc, const b200ocl_net_state* 
   size_t blocks = (p.n_params + 255) / 256;
   const size_t cap = (size_t)8 * sm_count();
   if (blocks > cap) blocks = cap;
+  B200OCL_PROF("sgd", 12.0 * p.n_params, stream);
   net_sgd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(st->params, st->grads, out_params, p.n_params, lr, weight_decay,
                                                        skip_lo, skip_hi);
   B200OCL_LAUNCHED();
@@ -486,6 +491,7 @@ int b200ocl_net_features_eval(const b200ocl_net_desc* desc, const b200ocl_net_st
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
   const int total = N * p.pooled_h * p.pooled_w * (desc->nf * 8);
+  B200OCL_PROF("pool", 4.0 * 17 * total, stream);
   pool_kernel<<<(total + 255) / 256, 256, 0, stream>>>(cur, feat, N, p.final_h, p.final_w, desc->nf * 8, p.pooled_h,
                                                        p.pooled_w);
   B200OCL_LAUNCHED();
@@ -532,10 +538,12 @@ int b200ocl_net_forward_train(const b200ocl_net_desc* desc, const b200ocl_net_st
     cur = w.a + (size_t)N * p.conv[B.c2].act_off;
   }
   if (st->bn_tracked) {
+    B200OCL_PROF("misc", 16.0 * p.n_conv, stream);
     bump_tracked_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<long long*>(st->bn_tracked), p.n_conv);
     B200OCL_LAUNCHED();
   }
   const int total = N * p.pooled_h * p.pooled_w * (desc->nf * 8);
+  B200OCL_PROF("pool", 4.0 * 17 * total, stream);
   pool_kernel<<<(total + 255) / 256, 256, 0, stream>>>(cur, w.feat, N, p.final_h, p.final_w, desc->nf * 8, p.pooled_h,
                                                        p.pooled_w);
   B200OCL_LAUNCHED();
@@ -547,6 +555,7 @@ int b200ocl_ce_loss(const float* logits, const int64_t* labels, int N, int C, fl
   using namespace b200ocl;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200OCL_CHECK_ARG(logits && labels && N >= 1 && C >= 1, "need logits, labels, N >= 1, C >= 1");
+  B200OCL_PROF("ce_loss", 8.0 * N * C, stream);
   ce_kernel<<<1, 256, 0, stream>>>(logits, reinterpret_cast<const long long*>(labels), N, C, loss, per_sample, dlogits,
                                    reinterpret_cast<long long*>(n_correct));
   B200OCL_LAUNCHED();

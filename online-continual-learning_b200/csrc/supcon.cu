@@ -253,10 +253,12 @@ int b200ocl_supcon(const float* feats, const int64_t* labels, int B, int V, int 
     B200OCL_CUDA(cudaFuncSetAttribute(supcon_grad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
+  B200OCL_PROF("supcon", 4.0 * p.A * d + 8.0 * B + 8.0 * p.A, stream);
   supcon_stats_kernel<<<grid, SC_THREADS, smem_stats, stream>>>(p);
   B200OCL_LAUNCHED();
   if (!dfeats) return B200OCL_OK;
 #define B200OCL_SC_GRAD(DCH) supcon_grad_kernel<DCH><<<grid, SC_THREADS, smem_grad, stream>>>(p)
+  B200OCL_PROF("supcon", 8.0 * p.A * d, stream);
   if (d <= 128) B200OCL_SC_GRAD(4);
   else if (d <= 256) B200OCL_SC_GRAD(8);
   else if (d <= 512) B200OCL_SC_GRAD(16);

@@ -94,6 +94,8 @@ class ContinualLearner(torch.nn.Module):
         else:
             self.engine = adopt(model, input_size_match[params.data][1])
         self.device = self.engine.device
+        self.grad_sync = None      # data-parallel stream shards: callable(engine) summing gradients over ranks
+        self.grad_world = 1
 
     def _lr_wd(self):
         """Step size / weight decay from the optimizer the caller built (run.py:40).  Only plain
@@ -107,6 +109,16 @@ class ContinualLearner(torch.nn.Module):
         if g.get('momentum', 0) or g.get('nesterov', False) or g.get('dampening', 0):
             raise NotImplementedError('SGD momentum/nesterov are not used by the reference and not implemented')
         return float(g['lr']), float(g['weight_decay'])
+
+    def _optimizer_step(self, lr, wd):
+        """opt.step(); with data-parallel stream shards the summed gradient is averaged first
+        (one all-reduce of the flat gradient arena, folded into the step size)."""
+        if self.grad_sync is not None:
+            self.grad_sync(self.engine)
+            if wd != 0.0:
+                raise NotImplementedError('weight decay with gradient averaging')
+            lr = lr / self.grad_world
+        self.engine.sgd_step(lr, wd)
 
     def before_train(self, x_train, y_train):
         new_labels = list(set(np.asarray(y_train).tolist()))
@@ -218,7 +230,7 @@ class ExperienceReplay(ContinualLearner):
                 self.last_loss = ce_c['loss']
             else:
                 self.last_loss = ce['loss']
-            eng.sgd_step(lr, wd)                                                    # :87 / :89
+            self._optimizer_step(lr, wd)                                            # :87 / :89
         self.buffer.update(batch_x, batch_y, y_host=batch_y_host)                   # :92
 
     def train_learner(self, x_train, y_train):
@@ -263,7 +275,7 @@ class SupContrastReplay(ContinualLearner):
                 loss, dfeat = ops.supcon(feats, labels, self.params.temp)           # :56  (base.py:109-111)
                 eng.backward(combined, dfeat[:, 0].contiguous(), ws1)               # :58-59
                 eng.backward(combined_aug, dfeat[:, 1].contiguous(), ws2, accumulate=True)
-                eng.sgd_step(lr, wd)                                                # :60
+                self._optimizer_step(lr, wd)                                        # :60
                 self.last_loss = loss
                 if meters is not None:
                     meters['losses'].update(loss, batch_y.size(0))

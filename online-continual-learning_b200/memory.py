@@ -174,6 +174,7 @@ class ClassBalancedRandomSampling:
 def random_retrieve(buffer, num_retrieve, excl_indices=None, return_indices=False):
     """buffer_utils.py:9-26."""
     idx = uniform_indices(buffer.current_index, num_retrieve, excl_indices)
+    buffer.last_random_idx = idx          # host record of the draw (tests replay it)
     x, y, idx_t = buffer.gather(idx)
     if return_indices:
         return x, y, idx_t

@@ -97,6 +97,7 @@ class ASER_retrieve(object):
         if self.aser_type != 'neg_sv':
             coop_ind = CB.sample_indices(self.n_smp_cls, excl_indices=cand_ind)
         n_cur, n_coop, n_cand = cur_x.shape[0], coop_ind.size, cand_ind.size
+        self.last_choices = {'ret_cand_ind': cand_ind, 'ret_coop_ind': coop_ind}
         # one batch [cur | coop | cand], one eval-mode feature pass
         batch = torch.empty((n_cur + n_coop + n_cand,) + tuple(cur_x.shape[1:]), dtype=torch.float32,
                             device=cur_x.device)
@@ -110,4 +111,5 @@ class ASER_retrieve(object):
                                    feats[n_cur + n_coop:], cand_y, self.k, self.aser_type,
                                    min(num_retrieve, n_cand))
         cand_x = batch[n_cur + n_coop:]
+        self.last_pos = pos
         return ops.gather_rows(cand_x, pos), ops.gather_rows(cand_y, pos)

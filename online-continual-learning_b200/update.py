@@ -54,6 +54,7 @@ class Reservoir_update(object):
                 return list(range(s, e))
         x, y, y_host = x[place_left:], y[place_left:], y_host[place_left:]
         draws = reservoir_draws(x.size(0), buffer.n_seen_so_far)
+        self.last_draws = draws
         buffer.n_seen_so_far += x.size(0)
         slots, src = reservoir_plan(draws, mem)
         if not slots:
@@ -103,6 +104,7 @@ class ASER_update(object):
     def minority_positions(self, cur_y_host):
         """aser_utils.py:148-157: threshold ~ U(0, 1/num_class) from the CPU torch generator."""
         threshold = torch.tensor(1).float().uniform_(0, 1 / self.out_dim).item()
+        self.last_threshold = threshold
         share = ClassBalancedRandomSampling.class_num_cache.astype(np.float32) / np.float32(self.mem_size)
         return np.flatnonzero(share[cur_y_host] < np.float32(threshold))
 
@@ -115,6 +117,7 @@ class ASER_update(object):
         eval_ind = CB.sample_indices(self.n_smp_cls)
         cand_ind = uniform_indices(buffer.current_index, self.n_total_smp, excl_indices=eval_ind)
         n_eval_buf, n_cand_buf = eval_ind.size, cand_ind.size
+        self.last_choices = {'upd_eval_ind': eval_ind, 'upd_cand_ind': cand_ind, 'upd_threshold': self.last_threshold}
         # one batch [eval_buf | cand_buf | cur]; candidates = [cand_buf | cur] are contiguous rows
         batch = torch.empty((n_eval_buf + n_cand_buf + n_cur,) + tuple(cur_x.shape[1:]), dtype=torch.float32, device=dev)
         idx_t = to_device_i64(np.concatenate([eval_ind, cand_ind]), dev)
