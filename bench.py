@@ -199,8 +199,11 @@ def run_ours(args, rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), _native.launch_count() - launches0, clocks, wall
 
+    log('rank %d: learners built' % rank)
     ms_dev, launches, clocks, wall = timed(False)
+    log('rank %d: device-resident pass %.2f ms/step' % (rank, ms_dev / args.steps))
     ms_e2e, _, _, _ = timed(True)
+    log('rank %d: end-to-end pass %.2f ms/step' % (rank, ms_e2e / args.steps))
     if rank != 0:
         return None
     imgs = 2 * BATCH * world * args.steps
@@ -292,13 +295,35 @@ def build_oracle_state(kind, seed):
     return st
 
 
-def run_reference(args, steps, warmup):
+def host_cores():
+    """Cores this process may actually use: affinity mask, capped by a cgroup CPU quota if one is set
+    (os.cpu_count() reports the machine, which oversubscribes torch's intra-op pool in a container)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as fh:
+            quota, period = fh.read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def log(msg):
+    print('[bench %7.1fs] %s' % (time.perf_counter() - T0, msg), file=sys.stderr, flush=True)
+
+
+T0 = time.perf_counter()
+
+
+def run_reference(args, steps, warmup, budget_s=30.0):
     """The reference's replay step on the host cores: oracle/replay_step.py (CPU, torch intra-op
     threads = all cores).  Each step is one ER+ASER step and one SCR step like the CUDA arm."""
     import torch
     from oracle import replay_step as ors
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
+    log('reference arm: %d host cores (os.cpu_count()=%s)' % (cores, os.cpu_count()))
     np.random.seed(0); torch.manual_seed(0)
     st_a, st_s = build_oracle_state('aser', 31), build_oracle_state('scr', 32)
     rs = np.random.RandomState(5)
@@ -310,11 +335,18 @@ def run_reference(args, steps, warmup):
         ors.scr_step(st_s, xs, ys, eps_mem_batch=100, temperature=0.07)
     for _ in range(warmup):
         step()
+    log('reference arm: warm-up done')
     t0 = time.perf_counter()
-    for _ in range(steps):
+    done = 0
+    while done < steps:
         step()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:       # bounded sample
+            break
     dt = time.perf_counter() - t0
-    return {'value': 2 * BATCH * steps / dt, 'unit': 'stream images/s', 'cores': cores, 'kind': 'port',
+    steps = done
+    log('reference arm: %d steps in %.1f s' % (steps, dt))
+    return {'steps': steps, 'value': 2 * BATCH * steps / dt, 'unit': 'stream images/s', 'cores': cores, 'kind': 'port',
             'sample': '%d steps (one ER+ASER + one SCR replay step each) of the same workload after %d warm-up, '
                       '%.1f s of CPU time, torch intra-op threads = %d' % (steps, warmup, dt, cores),
             'ms_per_step': 1e3 * dt / steps}
@@ -335,8 +367,9 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        steps, warmup = min(args.steps, 12), min(args.warmup, 2)
-        r = run_reference(args, steps, warmup)
+        steps, warmup = min(args.steps, 12), min(args.warmup, 1)
+        r = run_reference(args, steps, warmup, budget_s=120.0)
+        steps = r['steps']
         line = {'impl': 'reference', 'metric': 'replay-step images/sec (ASER+SCR, ResNet18, CIFAR100)',
                 'value': r['value'], 'unit': 'stream images/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
                 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
