@@ -180,6 +180,13 @@ int b200ocl_ce_loss(const float* logits, const int64_t* labels, int N, int C, fl
  * The random draws are the caller's; kornia's exact arithmetic is parity-unpinned (absent). */
 int b200ocl_scr_augment(const float* x, float* out, const float* params, int N, int H, int W, void* stream);
 
+/* ---------------------------------------------------------------- tensor-core self test
+ * D[128,N] = A[128,K] * B[N,K]^T on tcgen05 (kind::tf32, TMEM accumulator) with the descriptor
+ * encodings the tensor-core convolution uses; mode 0 single TF32 pass, mode 1 the 3xTF32 split.
+ * status[0] = 0 on completion, 1 if the MMA completion barrier timed out. */
+int b200ocl_selftest_umma_tf32(const float* A, const float* B, float* D, int N, int K, int mode, int* status,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

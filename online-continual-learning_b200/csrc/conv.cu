@@ -43,12 +43,13 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 // Shared epilogue: thread holds acc[PT][20] for rows r = row_base + 32*p (p < PT) and
 // channels n0 + wn*20 .. +19.  `scratch` is >= 4*20*2 doubles of shared memory, free to use.
-template <int BN, int PT>
+template <int BN, int PT, int WM = 4 / (BN / 20)>
 __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT][20], int m0, int n0, int row_base,
-                                              int wm, int wn, int lane, int tid, double* scratch) {
-  constexpr int WN = BN / 20, WM = 4 / WN;
+                                              int wm, int wn, int lane, int tid, double* scratch,
+                                              bool participates = true) {
   const int cbase = n0 + wn * 20;
   if (a.mode == CONV_EVAL) {
+    if (!participates) return;
     float sc[20], mu[20], be[20];
 #pragma unroll
     for (int c = 0; c < 20; ++c) {
@@ -86,7 +87,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT
 #pragma unroll
   for (int p = 0; p < PT; ++p) {
     const int m = m0 + row_base + 32 * p;
-    if (m >= a.M) continue;
+    if (m >= a.M || !participates) continue;
     float* o = a.out + (size_t)m * a.CN + cbase;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -108,7 +109,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT
 #pragma unroll
     for (int p = 0; p < PT; ++p) {
       const int m = m0 + row_base + 32 * p;
-      if (m < a.M) {
+      if (m < a.M && participates) {
         const double v = (double)acc[p][c];
         s += v;
         q += v * v;
@@ -116,7 +117,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT
     }
     s = warp_sum_d(s);
     q = warp_sum_d(q);
-    if (lane == 0) {
+    if (lane == 0 && participates) {
       s_stat[((wm * BN) + wn * 20 + c) * 2 + 0] = s;
       s_stat[((wm * BN) + wn * 20 + c) * 2 + 1] = q;
     }
@@ -178,7 +179,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT
 }
 
 template <int BN, int PT>
-__global__ void __launch_bounds__(CONV_THREADS) conv_kernel(ConvArgs a) {
+__global__ void __launch_bounds__(CONV_THREADS, (PT <= 2 ? 4 : 3)) conv_kernel(ConvArgs a) {
   constexpr int WN = BN / 20, WM = 4 / WN, BM = WM * 32 * PT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sA = reinterpret_cast<float*>(smem_raw);  // [2][BM][20]
@@ -215,8 +216,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_kernel(ConvArgs a) {
     const int tap = c / cpk, ci0 = (c - tap * cpk) * 20;
     const int kh = tap / a.ks, kw = tap - kh * a.ks;
     float* dA = sA + buf * BM * 20;
-    for (int idx = tid; idx < BM * 5; idx += CONV_THREADS) {
-      const int r = idx / 5, q = idx - r * 5;
+    for (int r = tid; r < BM; r += CONV_THREADS) {   // one thread stages a whole 80-byte row
       int hi, wi;
       bool ok;
       if (!a.transposed) {
@@ -236,8 +236,11 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_kernel(ConvArgs a) {
         }
         ok = ok && hi < a.Hin && wi < a.Win;
       }
-      const float* src = ok ? a.in + ((size_t)(s_base[r] + hi * a.Win + wi) * a.CK + ci0 + q * 4) : a.in;
-      cp_async16(dA + r * 20 + q * 4, src, ok ? 16 : 0);
+      const float* src = ok ? a.in + ((size_t)(s_base[r] + hi * a.Win + wi) * a.CK + ci0) : a.in;
+      const int nb = ok ? 16 : 0;
+      float* dst = dA + r * 20;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) cp_async16(dst + q * 4, ok ? src + q * 4 : src, nb);
     }
     float* dB = sB + buf * 20 * BN;
     const float* wsrc = a.w + ((size_t)tap * a.CK + ci0) * a.CN + n0;
@@ -337,6 +340,172 @@ __global__ void __launch_bounds__(CONV_THREADS) stem_kernel(ConvArgs a) {
   conv_epilogue<20, 1>(a, acc, m0, 0, warp * 32 + lane, warp, 0, lane, tid, scratch);
 }
 
+
+// Small-M variant: when the pixel count cannot fill the GPU the K loop is the critical path
+// (72 chunks for the 160-channel layers).  Here a CTA owns only 32*PT pixels x 20 channels and its
+// four warps each take every fourth (tap, 20-channel) chunk; partial sums meet in shared memory in
+// warp order (deterministic) and warp 0 runs the epilogue.  4x shorter dependency chain, 4-8x more CTAs.
+template <int PT>
+__global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a) {
+  constexpr int BM = 32 * PT, BN = 20, KS = 4;
+  constexpr int SLOT = BM * 20 + 20 * BN;  // floats per (stage, k-slot): A chunk then B chunk
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sbuf = reinterpret_cast<float*>(smem_raw);            // [2][KS][SLOT]
+  int* s_base = reinterpret_cast<int*>(sbuf + 2 * KS * SLOT);  // [BM]
+  int* s_h0 = s_base + BM;
+  int* s_w0 = s_h0 + BM;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int hw_out = a.Hout * a.Wout;
+  for (int r = tid; r < BM; r += CONV_THREADS) {
+    const int m = m0 + r;
+    if (m < a.M) {
+      const int n = m / hw_out, rem = m - n * hw_out;
+      const int ho = rem / a.Wout, wo = rem - ho * a.Wout;
+      s_base[r] = n * a.Hin * a.Win;
+      s_h0[r] = a.transposed ? ho + a.pad : ho * a.stride - a.pad;
+      s_w0[r] = a.transposed ? wo + a.pad : wo * a.stride - a.pad;
+    } else {
+      s_base[r] = 0;
+      s_h0[r] = -(1 << 20);
+      s_w0[r] = -(1 << 20);
+    }
+  }
+  __syncthreads();
+  const int cpk = a.CK / 20;
+  const int nchunks = a.ks * a.ks * cpk;
+  const int niter = (nchunks + KS - 1) / KS;
+
+  // all threads stage the (up to) four chunks of iteration `it` into stage `buf`
+  auto load_iter = [&](int it, int buf) {
+    for (int slot = 0; slot < KS; ++slot) {
+      const int c = it * KS + slot;
+      if (c >= nchunks) break;
+      const int tap = c / cpk, ci0 = (c - tap * cpk) * 20;
+      const int kh = tap / a.ks, kw = tap - kh * a.ks;
+      float* dA = sbuf + (buf * KS + slot) * SLOT;
+      for (int r = tid; r < BM; r += CONV_THREADS) {
+        int hi, wi;
+        bool ok;
+        if (!a.transposed) {
+          hi = s_h0[r] + kh;
+          wi = s_w0[r] + kw;
+          ok = (unsigned)hi < (unsigned)a.Hin && (unsigned)wi < (unsigned)a.Win;
+        } else {
+          const int th = s_h0[r] - kh, tw = s_w0[r] - kw;
+          ok = (th >= 0) && (tw >= 0);
+          if (a.stride == 2) {
+            ok = ok && (((th | tw) & 1) == 0);
+            hi = th >> 1;
+            wi = tw >> 1;
+          } else {
+            hi = th;
+            wi = tw;
+          }
+          ok = ok && hi < a.Hin && wi < a.Win;
+        }
+        const float* src = ok ? a.in + ((size_t)(s_base[r] + hi * a.Win + wi) * a.CK + ci0) : a.in;
+        const int nb = ok ? 16 : 0;
+        float* dst = dA + r * 20;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) cp_async16(dst + q * 4, ok ? src + q * 4 : src, nb);
+      }
+      float* dB = dA + BM * 20;
+      const float* wsrc = a.w + ((size_t)tap * a.CK + ci0) * a.CN + n0;
+      for (int idx = tid; idx < 20 * (BN / 4); idx += CONV_THREADS) {
+        const int kk = idx / (BN / 4), q = idx - kk * (BN / 4);
+        cp_async16(dB + kk * BN + q * 4, wsrc + (size_t)kk * a.CN + q * 4, 16);
+      }
+    }
+  };
+
+  float acc[PT][20];
+#pragma unroll
+  for (int p = 0; p < PT; ++p)
+#pragma unroll
+    for (int c = 0; c < 20; ++c) acc[p][c] = 0.f;
+
+  load_iter(0, 0);
+  cp_async_commit();
+  for (int it = 0; it < niter; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < niter) {
+      load_iter(it + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (it * KS + warp < nchunks) {
+      const float* pA = sbuf + (buf * KS + warp) * SLOT + lane * 20;
+      const float* pB = sbuf + (buf * KS + warp) * SLOT + BM * 20;
+#pragma unroll
+      for (int k4 = 0; k4 < 5; ++k4) {
+        float4 av[PT];
+#pragma unroll
+        for (int p = 0; p < PT; ++p) av[p] = *reinterpret_cast<const float4*>(pA + p * 32 * 20 + k4 * 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float w[20];
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            *reinterpret_cast<float4*>(&w[4 * j]) = *reinterpret_cast<const float4*>(pB + (k4 * 4 + kk) * BN + 4 * j);
+#pragma unroll
+          for (int p = 0; p < PT; ++p) {
+            const float x = kk == 0 ? av[p].x : (kk == 1 ? av[p].y : (kk == 2 ? av[p].z : av[p].w));
+#pragma unroll
+            for (int cc = 0; cc < 20; ++cc) acc[p][cc] = fmaf(x, w[cc], acc[p][cc]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // fixed-order combine of the four K-partials: warps 1..3 publish, warp 0 adds them in warp order
+  float* red = sbuf;  // [3][BM][20]  (all staging buffers are free now)
+  if (warp > 0) {
+#pragma unroll
+    for (int p = 0; p < PT; ++p)
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        *reinterpret_cast<float4*>(red + ((warp - 1) * BM + lane + 32 * p) * 20 + 4 * j) =
+            make_float4(acc[p][4 * j], acc[p][4 * j + 1], acc[p][4 * j + 2], acc[p][4 * j + 3]);
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 0; w < 3; ++w)
+#pragma unroll
+      for (int p = 0; p < PT; ++p)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(red + (w * BM + lane + 32 * p) * 20 + 4 * j);
+          acc[p][4 * j] += v.x; acc[p][4 * j + 1] += v.y; acc[p][4 * j + 2] += v.z; acc[p][4 * j + 3] += v.w;
+        }
+  }
+  __syncthreads();
+  conv_epilogue<20, PT, 1>(a, acc, m0, n0, lane, 0, 0, lane, tid, reinterpret_cast<double*>(smem_raw), warp == 0);
+}
+
+template <int PT>
+int launch_conv_ksplit(const ConvArgs& a, cudaStream_t stream) {
+  constexpr int BM = 32 * PT;
+  constexpr size_t smem = (size_t)(2 * 4 * (BM * 20 + 400)) * sizeof(float) + 3 * BM * sizeof(int);
+  static bool configured = false;
+  if (!configured) {
+    B200OCL_CUDA(cudaFuncSetAttribute(conv_ksplit_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((a.M + BM - 1) / BM, a.CN / 20);
+  B200OCL_PROF(a.transposed ? "conv_dgrad" : (a.mode == CONV_EVAL ? "conv_eval" : "conv_train"),
+               2.0 * a.M * (double)a.CN * a.CK * a.ks * a.ks, stream);
+  conv_ksplit_kernel<PT><<<grid, CONV_THREADS, smem, stream>>>(a);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
+
 template <int BN, int PT>
 int launch_conv_cfg(const ConvArgs& a, cudaStream_t stream) {
   constexpr int WN = BN / 20, WM = 4 / WN, BM = WM * 32 * PT;
@@ -362,28 +531,28 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     set_error("launch_conv: channel counts must be multiples of 20 (CK=%d CN=%d M=%d)", a.CK, a.CN, a.M);
     return B200OCL_EUNSUPPORTED;
   }
-  // Pick (BN, PT): the largest tile that still gives >= 2 CTAs per SM; otherwise the tiling with most CTAs.
-  const int target = 2 * sm_count();
+  // Tiling: the kernels are latency-sensitive (4 warps per CTA, LDS -> FMA chains), so the first goal is
+  // >= 4 resident CTAs per SM (16 warps); among tilings that reach it prefer wide channel tiles (the
+  // gathered pixel rows are shared by BN/20 warps) and 2-4 pixels per thread (weight loads amortised).
+  // When the pixel count cannot provide that many CTAs the K loop is split inside the CTA instead.
+  const long want = 4L * sm_count();
   const int bns[3] = {80, 40, 20};
-  const int pts[3] = {4, 2, 1};
-  int best_bn = 20, best_pt = 1;
-  long best_ctas = -1;
-  bool found = false;
-  for (int bi = 0; bi < 3 && !found; ++bi) {
-    const int bn = bns[bi];
-    if (a.CN % bn) continue;
-    for (int pi = 0; pi < 3; ++pi) {
-      const int pt = pts[pi];
-      const int bm = (80 / bn) * 32 * pt;
-      const long ctas = (long)((a.M + bm - 1) / bm) * (a.CN / bn);
-      if (ctas >= target) {
-        best_bn = bn; best_pt = pt; found = true;
-        break;
-      }
-      if (ctas > best_ctas) {
-        best_ctas = ctas; best_bn = bn; best_pt = pt;
-      }
+  auto ctas_reg = [&](int bn, int pt) {
+    const int bm = (80 / bn) * 32 * pt;
+    return (long)((a.M + bm - 1) / bm) * (a.CN / bn);
+  };
+  int best_bn = 0, best_pt = 0;
+  for (int bi = 0; bi < 3 && !best_bn; ++bi)
+    if (a.CN % bns[bi] == 0 && ctas_reg(bns[bi], 4) >= 2 * want) { best_bn = bns[bi]; best_pt = 4; }
+  for (int bi = 0; bi < 3 && !best_bn; ++bi)
+    if (a.CN % bns[bi] == 0 && ctas_reg(bns[bi], 2) >= want) { best_bn = bns[bi]; best_pt = 2; }
+  if (!best_bn) {
+    if (a.ks * a.ks * (a.CK / 20) >= 4) {
+      const long ctas2 = (long)((a.M + 63) / 64) * (a.CN / 20);
+      return ctas2 >= want ? launch_conv_ksplit<2>(a, stream) : launch_conv_ksplit<1>(a, stream);
     }
+    best_bn = 20;   // 1x1 convolutions with a short K: most CTAs
+    best_pt = 1;
   }
 #define B200OCL_CONV_CASE(BN_, PT_) \
   if (best_bn == BN_ && best_pt == PT_) return launch_conv_cfg<BN_, PT_>(a, stream)

@@ -194,7 +194,7 @@ struct WgradArgs {
 
 constexpr int WG_MC = 16;  // pixels staged per iteration
 
-__global__ void __launch_bounds__(384) wgrad_kernel(WgradArgs a) {
+__global__ void __launch_bounds__(128, 4) wgrad_kernel(WgradArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int KS = a.kw * 128;  // floats of K staged per pixel
   const int NS = a.nw * 20;
@@ -575,7 +575,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
   if ((rc = bn_backward(0, g0, w.a + (size_t)N * p.conv[0].act_off, w.g2, nullptr))) return rc;
   {
     const int M = N * p.in_h * p.in_w;
-    const int ctas = 2 * sms;
+    const int ctas = 8 * sms;
     const int ppc = (M + ctas - 1) / ctas;
     const int grid = (M + ppc - 1) / ppc;
     B200OCL_PROF("wgrad", 2.0 * M * 540.0, stream);
@@ -592,7 +592,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
       t.e[i].splits = (i == 0) ? grid : wgrad_cfg(p.conv[i], N, sms).splits;
     }
     B200OCL_PROF("wgrad_finalize", 8.0 * p.n_packed / 2, stream);
-    wgrad_finalize_kernel<<<dim3(32, p.n_conv), 256, 0, stream>>>(t, w.wg_part, st->grads, accumulate);
+    wgrad_finalize_kernel<<<dim3(128, p.n_conv), 256, 0, stream>>>(t, w.wg_part, st->grads, accumulate);
     B200OCL_LAUNCHED();
   }
   return B200OCL_OK;

@@ -39,13 +39,15 @@ inline WgradCfg wgrad_cfg(const ConvL& c, int N, int sms) {
   g.k4_groups = g.k_total / 4;
   const int k_tiles = (g.k4_groups + 31) / 32;
   const int n_groups = c.cout / 20;
-  g.kw = k_tiles < 3 ? k_tiles : 3;
-  g.nw = n_groups < 4 ? n_groups : 4;
+  g.kw = k_tiles < 2 ? k_tiles : 2;
+  g.nw = n_groups < 2 ? n_groups : 2;
   g.grid_k = (k_tiles + g.kw - 1) / g.kw;
   g.grid_n = (n_groups + g.nw - 1) / g.nw;
   const int M = N * c.hout * c.wout;
-  int splits = (4 * sms) / (g.grid_k * g.grid_n);
-  const int max_by_pixels = (M + 127) / 128;  // at least 128 pixels per CTA
+  // >= 16 resident warps per SM overall, at least 64 pixels of reduction per CTA
+  const int warps_per_cta = g.kw * g.nw;
+  int splits = (16 * sms + warps_per_cta * g.grid_k * g.grid_n - 1) / (warps_per_cta * g.grid_k * g.grid_n);
+  const int max_by_pixels = (M + 63) / 64;
   if (splits > max_by_pixels) splits = max_by_pixels;
   if (splits < 1) splits = 1;
   g.pix_per_split = ((M + splits - 1) / splits + 15) / 16 * 16;
@@ -121,7 +123,7 @@ inline TrainWs train_ws(const NetPlan& p, int N, void* base, int sms) {
   for (int i = 0; i < p.n_conv; ++i) {
     w.wg_off[i] = wg;
     if (i == 0) {
-      wg += (size_t)(2 * sms) * 27 * 20;  // stem: one partial per CTA
+      wg += (size_t)(8 * sms) * 27 * 20;  // stem: one partial per CTA
     } else {
       const WgradCfg g = wgrad_cfg(p.conv[i], N, sms);
       wg += (size_t)g.splits * g.k_total * p.conv[i].cout;

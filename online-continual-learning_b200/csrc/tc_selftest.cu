@@ -1,0 +1,122 @@
+// tc_selftest.cu -- minimal tcgen05 (kind::tf32, SS operands, TMEM accumulator) GEMM used to validate
+// the descriptor encodings of umma.cuh on the device before the tensor-core convolution relies on them.
+//   D[128, N] = A[128, K] * B[N, K]^T     K multiple of 32, N multiple of 16 in [16, 256]
+// mode 0: single TF32 pass (inputs truncated by the hardware); mode 1: 3xTF32 split
+// (hi*hi + hi*lo + lo*hi), the numerics the convolution uses.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace b200ocl {
+namespace {
+
+__global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                            float* __restrict__ D, int N, int K, int mode,
+                                                            int* __restrict__ status) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // [A_hi | A_lo | B_hi | B_lo], each a swizzled K-major tile of 32 fp32 per row
+  float* sAh = reinterpret_cast<float*>(smem_raw);
+  float* sAl = sAh + 128 * 32;
+  float* sBh = sAl + 128 * 32;
+  float* sBl = sBh + 256 * 32;
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_slot, ncols);
+  if (tid == 0) {
+    umma::mbar_init(&mbar, 1);
+    umma::fence_mbar_init();
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t idesc = umma::make_idesc_tf32(128, N);
+  uint32_t phase = 0;
+  bool ok = true;
+
+  for (int kb = 0; kb < K / 32; ++kb) {
+    // stage the K block: 16-byte chunks into the swizzled layout, split into hi / lo
+    for (int idx = tid; idx < 128 * 8; idx += 128) {
+      const int r = idx >> 3, c = idx & 7;
+      const float4 v = *reinterpret_cast<const float4*>(A + (size_t)r * K + kb * 32 + c * 4);
+      float4 h, l;
+      umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
+      umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+      const int off = umma::sw128_offset_f32(r, c);
+      *reinterpret_cast<float4*>(sAh + off) = (mode == 0) ? v : h;
+      *reinterpret_cast<float4*>(sAl + off) = l;
+    }
+    for (int idx = tid; idx < N * 8; idx += 128) {
+      const int r = idx >> 3, c = idx & 7;
+      const float4 v = *reinterpret_cast<const float4*>(B + (size_t)r * K + kb * 32 + c * 4);
+      float4 h, l;
+      umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
+      umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+      const int off = umma::sw128_offset_f32(r, c);
+      *reinterpret_cast<float4*>(sBh + off) = (mode == 0) ? v : h;
+      *reinterpret_cast<float4*>(sBl + off) = l;
+    }
+    umma::fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_thread_sync();
+      const uint64_t dAh = umma::make_smem_desc_sw128(umma::smem_u32(sAh));
+      const uint64_t dAl = umma::make_smem_desc_sw128(umma::smem_u32(sAl));
+      const uint64_t dBh = umma::make_smem_desc_sw128(umma::smem_u32(sBh));
+      const uint64_t dBl = umma::make_smem_desc_sw128(umma::smem_u32(sBl));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 32 bytes per K step, in 16-byte units
+        umma::mma_tf32_ss(tmem, dAh + adv, dBh + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        if (mode == 1) {
+          umma::mma_tf32_ss(tmem, dAh + adv, dBl + adv, idesc, 1u);
+          umma::mma_tf32_ss(tmem, dAl + adv, dBh + adv, idesc, 1u);
+        }
+      }
+      umma::mma_commit(&mbar);
+    }
+    // everybody waits for the MMAs before the staging buffers are overwritten
+    if (!umma::mbar_wait(&mbar, phase)) ok = false;
+    phase ^= 1;
+    __syncthreads();
+    if (!ok) break;
+  }
+  umma::fence_after_thread_sync();
+  if (ok) {
+    // warp w owns TMEM lanes 32w .. 32w+31 = output rows
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16];
+      umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) D[(size_t)row * N + c0 + j] = v[j];
+    }
+  }
+  if (tid == 0) *status = ok ? 0 : 1;
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
+}  // namespace
+}  // namespace b200ocl
+
+extern "C" int b200ocl_selftest_umma_tf32(const float* A, const float* B, float* D, int N, int K, int mode, int* status,
+                                          void* stream_) {
+  using namespace b200ocl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200OCL_CHECK_ARG(A && B && D && status, "null pointer");
+  B200OCL_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && K >= 32 && K % 32 == 0, "need N in [16,256] %16, K %32");
+  const size_t smem = (size_t)(2 * 128 * 32 + 2 * 256 * 32) * sizeof(float) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200OCL_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  umma_selftest_kernel<<<1, 128, smem, stream>>>(A, B, D, N, K, mode, status);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}

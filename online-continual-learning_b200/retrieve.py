@@ -52,6 +52,7 @@ class MIR_retrieve(object):
         post = ce_loss(logits_post, sub_y, want_grad=False, want_per_sample=True)['per_sample']
         big_ind = ops.rank_desc(post, self.num_retrieve, sa=1.0, b=pre, sb=-1.0)   # scores = post - pre
         self.last_scores = (pre, post)
+        self.last_top = big_ind
         return ops.gather_rows(sub_x, big_ind), ops.gather_rows(sub_y, big_ind)
 
 
