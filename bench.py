@@ -139,8 +139,10 @@ def run_ours(args, rank, world):
     dev = torch.device('cuda', local)
     np.random.seed(1000 + rank)
     torch.manual_seed(1000 + rank)
-    aser = build_learner('aser', 10 + rank)
-    scr = build_learner('scr', 20 + rank)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):       # stdout carries exactly one JSON line
+        aser = build_learner('aser', 10 + rank)
+        scr = build_learner('scr', 20 + rank)
     if world > 1:
         # same initial weights on every rank, then gradient averaging keeps the replicas identical
         for L in (aser, scr):

@@ -44,7 +44,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // Shared epilogue: thread holds acc[PT][20] for rows r = row_base + 32*p (p < PT) and
 // channels n0 + wn*20 .. +19.  `scratch` is >= 4*20*2 doubles of shared memory, free to use.
 template <int BN, int PT, int WM = 4 / (BN / 20)>
-__device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT][20], int m0, int n0, int row_base,
+__device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT][20], const int (&mrow)[PT], int n0,
                                               int wm, int wn, int lane, int tid, double* scratch,
                                               bool participates = true) {
   const int cbase = n0 + wn * 20;
@@ -60,8 +60,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT
     }
 #pragma unroll
     for (int p = 0; p < PT; ++p) {
-      const int m = m0 + row_base + 32 * p;
-      if (m >= a.M) continue;
+      const int m = mrow[p];
+      if (m < 0) continue;
       float* o = a.out + (size_t)m * a.CN + cbase;
       const float* rs = a.residual ? a.residual + (size_t)m * a.CN + cbase : nullptr;
 #pragma unroll
@@ -86,8 +86,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT
   // RAW / TRAIN / ACCUM: store (or add) the accumulators
 #pragma unroll
   for (int p = 0; p < PT; ++p) {
-    const int m = m0 + row_base + 32 * p;
-    if (m >= a.M || !participates) continue;
+    const int m = mrow[p];
+    if (m < 0 || !participates) continue;
     float* o = a.out + (size_t)m * a.CN + cbase;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -108,8 +108,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT
     double s = 0.0, q = 0.0;
 #pragma unroll
     for (int p = 0; p < PT; ++p) {
-      const int m = m0 + row_base + 32 * p;
-      if (m < a.M && participates) {
+      if (mrow[p] >= 0 && participates) {
         const double v = (double)acc[p][c];
         s += v;
         q += v * v;
@@ -146,11 +145,23 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT
   const int ch = tid % BN, grp = tid / BN;
   double s = 0.0, q = 0.0;
   if (grp < GROUPS) {
-    for (unsigned int b = grp; b < gridDim.x; b += GROUPS) {
-      const double* src = a.stat_part + ((size_t)b * a.CN + n0 + ch) * 2;
-      s += __ldcg(src);
-      q += __ldcg(src + 1);
+    double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned int b = grp;
+    for (; b + 3 * GROUPS < gridDim.x; b += 4 * GROUPS) {      // four loads in flight, fixed association
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(a.stat_part + ((size_t)(b + u * GROUPS) * a.CN + n0 + ch) * 2));
+        s4[u] += v.x;
+        q4[u] += v.y;
+      }
     }
+    for (; b < gridDim.x; b += GROUPS) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(a.stat_part + ((size_t)b * a.CN + n0 + ch) * 2));
+      s4[0] += v.x;
+      q4[0] += v.y;
+    }
+    s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
   }
   __syncthreads();  // s_stat reuse
   double* s_fin = scratch;  // [GROUPS][BN][2]
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(CONV_THREADS, (PT <= 2 ? 4 : 3)) conv_kernel(C
       for (int q = 0; q < 5; ++q) cp_async16(dst + q * 4, ok ? src + q * 4 : src, nb);
     }
     float* dB = sB + buf * 20 * BN;
-    const float* wsrc = a.w + ((size_t)tap * a.CK + ci0) * a.CN + n0;
+    const float* wsrc = a.w + ((size_t)(a.flip ? a.ks * a.ks - 1 - tap : tap) * a.CK + ci0) * a.CN + n0;
     for (int idx = tid; idx < 20 * (BN / 4); idx += CONV_THREADS) {
       const int kk = idx / (BN / 4), q = idx - kk * (BN / 4);
       cp_async16(dB + kk * BN + q * 4, wsrc + (size_t)kk * a.CN + q * 4, 16);
@@ -292,7 +303,10 @@ __global__ void __launch_bounds__(CONV_THREADS, (PT <= 2 ? 4 : 3)) conv_kernel(C
     }
     __syncthreads();
   }
-  conv_epilogue<BN, PT>(a, acc, m0, n0, row_base, wm, wn, lane, tid, reinterpret_cast<double*>(smem_raw));
+  int mrow[PT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) mrow[p] = (m0 + row_base + 32 * p < a.M) ? m0 + row_base + 32 * p : -1;
+  conv_epilogue<BN, PT>(a, acc, mrow, n0, wm, wn, lane, tid, reinterpret_cast<double*>(smem_raw));
 }
 
 // Stem: 3 -> 20 channels, 3x3, stride 1, pad 1, NCHW input read directly (no layout pass).
@@ -337,7 +351,8 @@ __global__ void __launch_bounds__(CONV_THREADS) stem_kernel(ConvArgs a) {
     }
   }
   // BN = 20, PT = 1: warp w owns rows 32*w + lane  (WM = 4, WN = 1)
-  conv_epilogue<20, 1>(a, acc, m0, 0, warp * 32 + lane, warp, 0, lane, tid, scratch);
+  const int mrow[1] = {m < a.M ? m : -1};
+  conv_epilogue<20, 1>(a, acc, mrow, 0, warp, 0, lane, tid, scratch);
 }
 
 
@@ -412,7 +427,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a
         for (int q = 0; q < 5; ++q) cp_async16(dst + q * 4, ok ? src + q * 4 : src, nb);
       }
       float* dB = dA + BM * 20;
-      const float* wsrc = a.w + ((size_t)tap * a.CK + ci0) * a.CN + n0;
+      const float* wsrc = a.w + ((size_t)(a.flip ? a.ks * a.ks - 1 - tap : tap) * a.CK + ci0) * a.CN + n0;
       for (int idx = tid; idx < 20 * (BN / 4); idx += CONV_THREADS) {
         const int kk = idx / (BN / 4), q = idx - kk * (BN / 4);
         cp_async16(dB + kk * BN + q * 4, wsrc + (size_t)kk * a.CN + q * 4, 16);
@@ -486,7 +501,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a
         }
   }
   __syncthreads();
-  conv_epilogue<20, PT, 1>(a, acc, m0, n0, lane, 0, 0, lane, tid, reinterpret_cast<double*>(smem_raw), warp == 0);
+  int mrow[PT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) mrow[p] = (m0 + lane + 32 * p < a.M) ? m0 + lane + 32 * p : -1;
+  conv_epilogue<20, PT, 1>(a, acc, mrow, n0, 0, 0, lane, tid, reinterpret_cast<double*>(smem_raw), warp == 0);
 }
 
 template <int PT>
@@ -502,6 +520,147 @@ int launch_conv_ksplit(const ConvArgs& a, cudaStream_t stream) {
   B200OCL_PROF(a.transposed ? "conv_dgrad" : (a.mode == CONV_EVAL ? "conv_eval" : "conv_train"),
                2.0 * a.M * (double)a.CN * a.CK * a.ks * a.ks, stream);
   conv_ksplit_kernel<PT><<<grid, CONV_THREADS, smem, stream>>>(a);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
+
+
+// Direct ("patch") variant for the forward 3x3 / 1x1 convolutions and the stride-1 data gradients:
+// a CTA owns a spatial tile of TI images x TH x TW output pixels and stages, per 20-channel slice of
+// the input, the input patch WITH its halo once (zero-filled outside the image) together with the
+// weights of all taps; the taps then read the same shared-memory patch at shifted offsets.  Compared
+// with the gather kernel above this removes the per-tap re-gather (9x less L2 traffic and address
+// arithmetic) and all but two barriers per 20 input channels.  flip = 1 turns it into the stride-1
+// data gradient (correlation with the spatially flipped taps of the [tap][cout][cin] weights).
+template <int BN, int PT>
+__global__ void __launch_bounds__(CONV_THREADS, (PT <= 2 ? 3 : 2)) conv_patch_kernel(ConvArgs a) {
+  constexpr int WN = BN / 20;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(16) double scratch[4 * 20 * 2 * 2];
+  const int taps = a.ks * a.ks;
+  const int PH = (a.th - 1) * a.stride + a.ks, PW = (a.tw - 1) * a.stride + a.ks;
+  const int prows = a.ti * PH * PW;
+  float* spatch = reinterpret_cast<float*>(smem_raw);   // [prows][20]
+  float* sW = spatch + prows * 20;                      // [taps*20][BN]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp / WN, wn = warp % WN;
+  const int n0 = blockIdx.y * BN;
+  int t = blockIdx.x;
+  const int tiles_x = (a.Wout + a.tw - 1) / a.tw, tiles_y = (a.Hout + a.th - 1) / a.th;
+  const int tx_i = t % tiles_x;
+  t /= tiles_x;
+  const int ty_i = t % tiles_y;
+  const int img0 = (t / tiles_y) * a.ti;
+  const int x0 = tx_i * a.tw, y0 = ty_i * a.th;
+  const int iy0 = y0 * a.stride - a.pad, ix0 = x0 * a.stride - a.pad;
+
+  int mrow[PT], prow0[PT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) {
+    const int r = wm * 32 * PT + lane + 32 * p;   // wm < 4 / WN pixel-warps
+    const int img = r / (a.th * a.tw), rem = r - img * (a.th * a.tw);
+    const int y = rem / a.tw, x = rem - y * a.tw;
+    const bool valid = (img < a.ti) && (img0 + img < a.N) && (y0 + y < a.Hout) && (x0 + x < a.Wout);
+    mrow[p] = valid ? ((img0 + img) * a.Hout + y0 + y) * a.Wout + x0 + x : -1;
+    prow0[p] = (img < a.ti) ? (img * PH + y * a.stride) * PW + x * a.stride : 0;
+  }
+
+  float acc[PT][20];
+#pragma unroll
+  for (int p = 0; p < PT; ++p)
+#pragma unroll
+    for (int c = 0; c < 20; ++c) acc[p][c] = 0.f;
+
+  const int nslices = a.CK / 20;
+  for (int cc = 0; cc < nslices; ++cc) {
+    __syncthreads();  // previous slice fully consumed
+    for (int row = tid; row < prows; row += CONV_THREADS) {
+      const int img = row / (PH * PW), rr = row - img * (PH * PW);
+      const int py = rr / PW, px = rr - py * PW;
+      const int iy = iy0 + py, ix = ix0 + px;
+      const bool ok = (img0 + img < a.N) && (unsigned)iy < (unsigned)a.Hin && (unsigned)ix < (unsigned)a.Win;
+      const float* src = ok ? a.in + ((size_t)((img0 + img) * a.Hin + iy) * a.Win + ix) * a.CK + cc * 20 : a.in;
+      const int nb = ok ? 16 : 0;
+      float* dst = spatch + row * 20;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) cp_async16(dst + q * 4, ok ? src + q * 4 : src, nb);
+    }
+    for (int idx = tid; idx < taps * 20 * (BN / 4); idx += CONV_THREADS) {
+      const int row = idx / (BN / 4), q = idx - row * (BN / 4);
+      const int tap = row / 20, kk = row - tap * 20;
+      const int wt = a.flip ? taps - 1 - tap : tap;
+      cp_async16(sW + row * BN + q * 4, a.w + ((size_t)wt * a.CK + cc * 20 + kk) * a.CN + n0 + q * 4, 16);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int tap = 0; tap < taps; ++tap) {
+      const int kh = tap / a.ks, kw = tap - kh * a.ks;
+      const float* pA = spatch + (kh * PW + kw) * 20;
+      const float* pB = sW + tap * 20 * BN + wn * 20;
+#pragma unroll
+      for (int k4 = 0; k4 < 5; ++k4) {
+        float4 av[PT];
+#pragma unroll
+        for (int p = 0; p < PT; ++p) av[p] = *reinterpret_cast<const float4*>(pA + prow0[p] * 20 + k4 * 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float w[20];
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            *reinterpret_cast<float4*>(&w[4 * j]) = *reinterpret_cast<const float4*>(pB + (k4 * 4 + kk) * BN + 4 * j);
+#pragma unroll
+          for (int p = 0; p < PT; ++p) {
+            const float x = kk == 0 ? av[p].x : (kk == 1 ? av[p].y : (kk == 2 ? av[p].z : av[p].w));
+#pragma unroll
+            for (int cc2 = 0; cc2 < 20; ++cc2) acc[p][cc2] = fmaf(x, w[cc2], acc[p][cc2]);
+          }
+        }
+      }
+    }
+  }
+  conv_epilogue<BN, PT>(a, acc, mrow, n0, wm, wn, lane, tid, scratch);
+}
+
+struct PatchTile {
+  int th, tw, ti;
+  long ctas;
+  size_t smem;
+};
+
+// Spatial tile of bm = 32*PT*WM output pixels: widest power-of-two strip of a row (<= 32), then rows,
+// then images.
+inline PatchTile patch_tile(const ConvArgs& a, int bn, int pt) {
+  PatchTile t{};
+  const int bm = (80 / bn) * 32 * pt;
+  int tw = 1;
+  while (tw * 2 <= a.Wout && tw < 32) tw *= 2;
+  if (tw > bm) tw = bm;
+  int hp = 1;
+  while (hp < a.Hout) hp *= 2;
+  int th = bm / tw;
+  if (th > hp) th = hp;
+  t.tw = tw; t.th = th; t.ti = bm / (tw * th);
+  const int PH = (th - 1) * a.stride + a.ks, PW = (tw - 1) * a.stride + a.ks;
+  const long tiles = (long)((a.N + t.ti - 1) / t.ti) * ((a.Hout + th - 1) / th) * ((a.Wout + tw - 1) / tw);
+  t.ctas = tiles * (a.CN / bn);
+  t.smem = ((size_t)t.ti * PH * PW * 20 + (size_t)a.ks * a.ks * 20 * bn) * sizeof(float);
+  return t;
+}
+
+template <int BN, int PT>
+int launch_conv_patch(ConvArgs a, const PatchTile& t, cudaStream_t stream) {
+  a.th = t.th; a.tw = t.tw; a.ti = t.ti;
+  static size_t configured = 0;
+  if (t.smem > configured) {
+    B200OCL_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+    configured = t.smem;
+  }
+  dim3 grid((unsigned)(t.ctas / (a.CN / BN)), a.CN / BN);
+  B200OCL_PROF(a.flip ? "conv_dgrad" : (a.mode == CONV_EVAL ? "conv_eval" : "conv_train"),
+               2.0 * a.M * (double)a.CN * a.CK * a.ks * a.ks, stream);
+  conv_patch_kernel<BN, PT><<<grid, CONV_THREADS, t.smem, stream>>>(a);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
 }
@@ -530,6 +689,24 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if (a.CK % 20 != 0 || a.CN % 20 != 0 || a.M <= 0) {
     set_error("launch_conv: channel counts must be multiples of 20 (CK=%d CN=%d M=%d)", a.CK, a.CN, a.M);
     return B200OCL_EUNSUPPORTED;
+  }
+  // Forward convolutions and stride-1 data gradients with enough pixels go to the patch kernel:
+  // pick the widest channel tile and 2 pixels per thread that still give >= 3 CTAs per SM.
+  if (!a.transposed && a.ks * a.ks * 20 * 80 * sizeof(float) <= 64 * 1024) {
+    const long want3 = 5L * sm_count() / 2;
+    const int pbn[3] = {80, 40, 20};
+    const int ppt[2] = {2, 1};
+    for (int pi = 0; pi < 2; ++pi)
+      for (int bi = 0; bi < 3; ++bi) {
+        if (a.CN % pbn[bi]) continue;
+        const PatchTile t = patch_tile(a, pbn[bi], ppt[pi]);
+        if (t.ctas < want3 || t.smem > 72 * 1024) continue;
+#define B200OCL_PATCH_CASE(BN_, PT_) \
+        if (pbn[bi] == BN_ && ppt[pi] == PT_) return launch_conv_patch<BN_, PT_>(a, t, stream)
+        B200OCL_PATCH_CASE(80, 2); B200OCL_PATCH_CASE(40, 2); B200OCL_PATCH_CASE(20, 2);
+        B200OCL_PATCH_CASE(80, 1); B200OCL_PATCH_CASE(40, 1); B200OCL_PATCH_CASE(20, 1);
+#undef B200OCL_PATCH_CASE
+      }
   }
   // Tiling: the kernels are latency-sensitive (4 warps per CTA, LDS -> FMA chains), so the first goal is
   // >= 4 resident CTAs per SM (16 warps); among tilings that reach it prefer wide channel tiles (the

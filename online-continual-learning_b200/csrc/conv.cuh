@@ -20,6 +20,8 @@ struct ConvArgs {
   int ks, stride, pad;
   int transposed;    // 0: forward gather (hi = ho*stride - pad + kh); 1: data-gradient gather
                      //    (input pixel (t/stride) with t = ho + pad - kh, only when divisible)
+  int flip;          // patch kernel only: use tap (ks*ks-1-tap) of the weights (stride-1 data gradient)
+  int th, tw, ti;    // patch kernel only: spatial tile (rows, cols, images), set by the launcher
   int M;             // N*Hout*Wout output pixels
   int mode;
   // CONV_EVAL

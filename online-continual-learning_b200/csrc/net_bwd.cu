@@ -543,9 +543,15 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     a.Hin = c.hout; a.Win = c.wout; a.CK = c.cout;
     a.Hout = c.hin; a.Wout = c.win; a.CN = c.cin;
     a.ks = c.ks; a.stride = c.stride; a.pad = c.pad;
-    a.transposed = 1;
     a.M = N * c.hin * c.win;
     a.mode = accum ? CONV_ACCUM : CONV_RAW;
+    if (c.stride == 1) {
+      // dx[h,w] = sum_taps dz[h+1-kh, w+1-kw] W[kh,kw]: a forward-style correlation with flipped taps
+      a.transposed = 0;
+      a.flip = 1;
+    } else {
+      a.transposed = 1;
+    }
     return launch_conv(a, stream);
   };
 

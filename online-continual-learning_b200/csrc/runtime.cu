@@ -1,5 +1,6 @@
 // runtime.cu -- error string, launch counter, device properties.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -83,9 +84,12 @@ int b200ocl_profile_end(void) {
   g_prof_on = false;
   cudaDeviceSynchronize();
   g_agg.clear();
+  FILE* dump = nullptr;
+  if (const char* path = getenv("B200OCL_PROF_DUMP")) dump = fopen(path, "a");   // one line per launch
   for (auto& r : g_recs) {
     float ms = 0.f;
     if (r.open || cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+    if (dump) fprintf(dump, "%s,%.1f,%.3f\n", r.name, r.work, ms * 1e3);
     bool found = false;
     for (auto& a : g_agg)
       if (a.name == r.name) { a.ms += ms; a.work += r.work; a.count += 1; found = true; break; }
@@ -93,6 +97,7 @@ int b200ocl_profile_end(void) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
+  if (dump) fclose(dump);
   g_recs.clear();
   (void)cudaGetLastError();
   return (int)g_agg.size();

@@ -48,5 +48,6 @@ def test_umma_3xtf32_is_fp32_grade(N, K):
     e1 = np.abs(D1 - ref).max() / scale
     e3 = np.abs(D3 - ref).max() / scale
     fp32 = np.abs((A @ B.T) - ref).max() / scale
+    print('K=%d  single-pass TF32 %.2e   3xTF32 %.2e   numpy fp32 %.2e' % (K, e1, e3, fp32))
     assert e1 > 1e-5          # a single TF32 pass is visibly lossy
-    assert e3 < 4e-6, (e3, fp32)   # the split is within a small factor of an fp32 GEMM
+    assert e3 < 8 * fp32 + 5e-7, (e3, fp32)   # the split is within a small factor of an fp32 GEMM
