@@ -193,9 +193,10 @@ template <int BN, int PT>
 __global__ void __launch_bounds__(CONV_THREADS, (PT <= 2 ? 4 : 3)) conv_kernel(ConvArgs a) {
   constexpr int WN = BN / 20, WM = 4 / WN, BM = WM * 32 * PT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sA = reinterpret_cast<float*>(smem_raw);  // [2][BM][20]
-  float* sB = sA + 2 * BM * 20;                    // [2][20][BN]
-  int* s_base = reinterpret_cast<int*>(sB + 2 * 20 * BN);
+  constexpr int NST = 3;
+  float* sA = reinterpret_cast<float*>(smem_raw);  // [NST][BM][20]
+  float* sB = sA + NST * BM * 20;                  // [NST][20][BN]
+  int* s_base = reinterpret_cast<int*>(sB + NST * 20 * BN);
   int* s_h0 = s_base + BM;
   int* s_w0 = s_h0 + BM;
 
@@ -268,18 +269,17 @@ __global__ void __launch_bounds__(CONV_THREADS, (PT <= 2 ? 4 : 3)) conv_kernel(C
     for (int c = 0; c < 20; ++c) acc[p][c] = 0.f;
 
   const int row_base = wm * 32 * PT + lane;
-  load_chunk(0, 0);
-  cp_async_commit();
+#pragma unroll
+  for (int st = 0; st < NST - 1; ++st) {
+    if (st < nchunks) load_chunk(st, st);
+    cp_async_commit();
+  }
   for (int c = 0; c < nchunks; ++c) {
-    const int buf = c & 1;
-    if (c + 1 < nchunks) {
-      load_chunk(c + 1, buf ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    const int buf = c % NST;
+    cp_async_wait<NST - 2>();
     __syncthreads();
+    if (c + NST - 1 < nchunks) load_chunk(c + NST - 1, (c + NST - 1) % NST);
+    cp_async_commit();
     const float* pA = sA + buf * BM * 20 + row_base * 20;
     const float* pB = sB + buf * 20 * BN + wn * 20;
 #pragma unroll
@@ -301,8 +301,9 @@ __global__ void __launch_bounds__(CONV_THREADS, (PT <= 2 ? 4 : 3)) conv_kernel(C
         }
       }
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  __syncthreads();
   int mrow[PT];
 #pragma unroll
   for (int p = 0; p < PT; ++p) mrow[p] = (m0 + row_base + 32 * p < a.M) ? m0 + row_base + 32 * p : -1;
@@ -363,10 +364,11 @@ __global__ void __launch_bounds__(CONV_THREADS) stem_kernel(ConvArgs a) {
 template <int PT>
 __global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a) {
   constexpr int BM = 32 * PT, BN = 20, KS = 4;
+  constexpr int NST = (PT == 1) ? 4 : 3;   // cp.async ring depth: the per-iteration math is shorter than one L2 round trip
   constexpr int SLOT = BM * 20 + 20 * BN;  // floats per (stage, k-slot): A chunk then B chunk
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sbuf = reinterpret_cast<float*>(smem_raw);            // [2][KS][SLOT]
-  int* s_base = reinterpret_cast<int*>(sbuf + 2 * KS * SLOT);  // [BM]
+  float* sbuf = reinterpret_cast<float*>(smem_raw);              // [NST][KS][SLOT]
+  int* s_base = reinterpret_cast<int*>(sbuf + NST * KS * SLOT);  // [BM]
   int* s_h0 = s_base + BM;
   int* s_w0 = s_h0 + BM;
 
@@ -441,18 +443,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a
 #pragma unroll
     for (int c = 0; c < 20; ++c) acc[p][c] = 0.f;
 
-  load_iter(0, 0);
-  cp_async_commit();
+#pragma unroll
+  for (int st = 0; st < NST - 1; ++st) {
+    if (st < niter) load_iter(st, st);
+    cp_async_commit();
+  }
   for (int it = 0; it < niter; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < niter) {
-      load_iter(it + 1, buf ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
+    const int buf = it % NST;
+    cp_async_wait<NST - 2>();
+    __syncthreads();   // stage `it` has landed; stage (it-1) is free for the prefetch below
+    if (it + NST - 1 < niter) load_iter(it + NST - 1, (it + NST - 1) % NST);
+    cp_async_commit();
     if (it * KS + warp < nchunks) {
       const float* pA = sbuf + (buf * KS + warp) * SLOT + lane * 20;
       const float* pB = sbuf + (buf * KS + warp) * SLOT + BM * 20;
@@ -476,8 +477,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a
         }
       }
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  __syncthreads();
   // fixed-order combine of the four K-partials: warps 1..3 publish, warp 0 adds them in warp order
   float* red = sbuf;  // [3][BM][20]  (all staging buffers are free now)
   if (warp > 0) {
@@ -510,7 +512,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a
 template <int PT>
 int launch_conv_ksplit(const ConvArgs& a, cudaStream_t stream) {
   constexpr int BM = 32 * PT;
-  constexpr size_t smem = (size_t)(2 * 4 * (BM * 20 + 400)) * sizeof(float) + 3 * BM * sizeof(int);
+  constexpr int NST = (PT == 1) ? 4 : 3;
+  constexpr size_t smem = (size_t)(NST * 4 * (BM * 20 + 400)) * sizeof(float) + 3 * BM * sizeof(int);
   static bool configured = false;
   if (!configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(conv_ksplit_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -668,7 +671,7 @@ int launch_conv_patch(ConvArgs a, const PatchTile& t, cudaStream_t stream) {
 template <int BN, int PT>
 int launch_conv_cfg(const ConvArgs& a, cudaStream_t stream) {
   constexpr int WN = BN / 20, WM = 4 / WN, BM = WM * 32 * PT;
-  constexpr size_t smem = (size_t)(2 * BM * 20 + 2 * 20 * BN) * sizeof(float) + 3 * BM * sizeof(int);
+  constexpr size_t smem = (size_t)(3 * BM * 20 + 3 * 20 * BN) * sizeof(float) + 3 * BM * sizeof(int);
   static bool configured = false;
   if (!configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(conv_kernel<BN, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -719,8 +722,6 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     return (long)((a.M + bm - 1) / bm) * (a.CN / bn);
   };
   int best_bn = 0, best_pt = 0;
-  for (int bi = 0; bi < 3 && !best_bn; ++bi)
-    if (a.CN % bns[bi] == 0 && ctas_reg(bns[bi], 4) >= 2 * want) { best_bn = bns[bi]; best_pt = 4; }
   for (int bi = 0; bi < 3 && !best_bn; ++bi)
     if (a.CN % bns[bi] == 0 && ctas_reg(bns[bi], 2) >= want) { best_bn = bns[bi]; best_pt = 2; }
   if (!best_bn) {

@@ -192,51 +192,49 @@ struct WgradArgs {
   int k_total, k4_groups, kw, nw, pix_per_split;
 };
 
-constexpr int WG_MC = 16;  // pixels staged per iteration
+constexpr int WG_MC = 16;   // pixels staged per iteration
+constexpr int WG_NST = 3;   // cp.async ring depth
 
-__global__ void __launch_bounds__(128, 4) wgrad_kernel(WgradArgs a) {
+__global__ void __launch_bounds__(128, 3) wgrad_kernel(WgradArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int KS = a.kw * 128;  // floats of K staged per pixel
   const int NS = a.nw * 20;
-  float* sA = smem;                 // [MC][KS]
-  float* sG = sA + WG_MC * KS;      // [MC][NS]
-  int* s_base = reinterpret_cast<int*>(sG + WG_MC * NS);  // [MC]
-  int* s_h0 = s_base + WG_MC;
-  int* s_w0 = s_h0 + WG_MC;
+  const int stage_f = WG_MC * (KS + NS);
+  float* sbuf = smem;                                              // [NST][ MC*KS | MC*NS ]
+  int* s_info = reinterpret_cast<int*>(sbuf + WG_NST * stage_f);   // [NST+1][3][MC]: base, h0, w0
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x;
   const int kwi = warp % a.kw, nwi = warp / a.kw;
-  const int g4_base = blockIdx.x * a.kw * 32;          // first k4-group of this CTA
-  const int co_base = blockIdx.y * NS;                 // first output channel of this CTA
+  const int g4_base = blockIdx.x * a.kw * 32;
+  const int co_base = blockIdx.y * NS;
   const int m_begin = blockIdx.z * a.pix_per_split;
   const int m_end = min(a.M, m_begin + a.pix_per_split);
   const int hw_out = a.Hout * a.Wout;
+  const int nch = (m_end - m_begin + WG_MC - 1) / WG_MC;
 
-  float acc[4][20];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int c = 0; c < 20; ++c) acc[i][c] = 0.f;
-
-  for (int m0 = m_begin; m0 < m_end; m0 += WG_MC) {
-    __syncthreads();  // previous chunk consumed
+  auto rowinfo = [&](int c) {   // threads < MC
     if (tid < WG_MC) {
-      const int m = m0 + tid;
-      if (m < m_end) {
+      int* inf = s_info + (c % (WG_NST + 1)) * 3 * WG_MC;
+      const int m = m_begin + c * WG_MC + tid;
+      if (c < nch && m < m_end) {
         const int n = m / hw_out, rem = m - n * hw_out;
         const int ho = rem / a.Wout, wo = rem - ho * a.Wout;
-        s_base[tid] = n * a.Hin * a.Win;
-        s_h0[tid] = ho * a.stride - a.pad;
-        s_w0[tid] = wo * a.stride - a.pad;
+        inf[tid] = n * a.Hin * a.Win;
+        inf[WG_MC + tid] = ho * a.stride - a.pad;
+        inf[2 * WG_MC + tid] = wo * a.stride - a.pad;
       } else {
-        s_base[tid] = 0;
-        s_h0[tid] = -(1 << 20);
-        s_w0[tid] = -(1 << 20);
+        inf[tid] = 0;
+        inf[WG_MC + tid] = -(1 << 20);
+        inf[2 * WG_MC + tid] = -(1 << 20);
       }
     }
-    __syncthreads();
-    // im2col gather: [MC pixels][kw*32 k4-groups] x 16 bytes
+  };
+  auto gather = [&](int c) {
+    const int* inf = s_info + (c % (WG_NST + 1)) * 3 * WG_MC;
+    float* sA = sbuf + (c % WG_NST) * stage_f;
+    float* sG = sA + WG_MC * KS;
+    const int m0 = m_begin + c * WG_MC;
     for (int idx = tid; idx < WG_MC * a.kw * 32; idx += nthreads) {
       const int pm = idx / (a.kw * 32), gl = idx - pm * (a.kw * 32);
       const int g4 = g4_base + gl;
@@ -246,9 +244,9 @@ __global__ void __launch_bounds__(128, 4) wgrad_kernel(WgradArgs a) {
         const int k = g4 * 4;
         const int tap = k / a.Cin, ci = k - tap * a.Cin;
         const int kh = tap / a.ks, kwd = tap - kh * a.ks;
-        const int hi = s_h0[pm] + kh, wi = s_w0[pm] + kwd;
+        const int hi = inf[WG_MC + pm] + kh, wi = inf[2 * WG_MC + pm] + kwd;
         ok = (unsigned)hi < (unsigned)a.Hin && (unsigned)wi < (unsigned)a.Win;
-        if (ok) src = a.x + ((size_t)(s_base[pm] + hi * a.Win + wi) * a.Cin + ci);
+        if (ok) src = a.x + ((size_t)(inf[pm] + hi * a.Win + wi) * a.Cin + ci);
       }
       cp_async16(sA + pm * KS + gl * 4, src, ok ? 16 : 0);
     }
@@ -259,10 +257,29 @@ __global__ void __launch_bounds__(128, 4) wgrad_kernel(WgradArgs a) {
       const float* src = ok ? a.dz + (size_t)m * a.Cout + co_base + q * 4 : a.dz;
       cp_async16(sG + pm * NS + q * 4, src, ok ? 16 : 0);
     }
-    cp_async_commit_wait_all();
+  };
+
+  float acc[4][20];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 20; ++c) acc[i][c] = 0.f;
+
+  for (int c = 0; c < WG_NST; ++c) rowinfo(c);
+  __syncthreads();
+#pragma unroll
+  for (int st = 0; st < WG_NST - 1; ++st) {
+    if (st < nch) gather(st);
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+  for (int c = 0; c < nch; ++c) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(WG_NST - 2));
     __syncthreads();
-    const float* pA = sA + kwi * 128 + lane * 4;
-    const float* pG = sG + nwi * 20;
+    rowinfo(c + WG_NST);                       // consumed by the gather of the NEXT iteration
+    if (c + WG_NST - 1 < nch) gather(c + WG_NST - 1);
+    asm volatile("cp.async.commit_group;\n" ::);
+    const float* pA = sbuf + (c % WG_NST) * stage_f + kwi * 128 + lane * 4;
+    const float* pG = sbuf + (c % WG_NST) * stage_f + WG_MC * KS + nwi * 20;
 #pragma unroll 4
     for (int pm = 0; pm < WG_MC; ++pm) {
       const float4 a4 = *reinterpret_cast<const float4*>(pA + pm * KS);
@@ -271,14 +288,15 @@ __global__ void __launch_bounds__(128, 4) wgrad_kernel(WgradArgs a) {
       for (int j = 0; j < 5; ++j)
         *reinterpret_cast<float4*>(&g[4 * j]) = *reinterpret_cast<const float4*>(pG + pm * NS + 4 * j);
 #pragma unroll
-      for (int c = 0; c < 20; ++c) {
-        acc[0][c] = fmaf(a4.x, g[c], acc[0][c]);
-        acc[1][c] = fmaf(a4.y, g[c], acc[1][c]);
-        acc[2][c] = fmaf(a4.z, g[c], acc[2][c]);
-        acc[3][c] = fmaf(a4.w, g[c], acc[3][c]);
+      for (int cc = 0; cc < 20; ++cc) {
+        acc[0][cc] = fmaf(a4.x, g[cc], acc[0][cc]);
+        acc[1][cc] = fmaf(a4.y, g[cc], acc[1][cc]);
+        acc[2][cc] = fmaf(a4.z, g[cc], acc[2][cc]);
+        acc[3][cc] = fmaf(a4.w, g[cc], acc[3][cc]);
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;\n" ::);
   const int g4 = g4_base + kwi * 32 + lane;
   const int co = co_base + nwi * 20;
   if (g4 < a.k4_groups && co < a.Cout) {
@@ -305,13 +323,28 @@ __global__ void __launch_bounds__(576) stem_wgrad_kernel(const float* __restrict
   const int m0 = blockIdx.x * pix_per_cta, m1 = min(M, m0 + pix_per_cta);
   float acc = 0.f;
   if (active) {
-    for (int m = m0; m < m1; ++m) {
-      const int n = m / hw, rem = m - n * hw;
-      const int ho = rem / W, wo = rem - ho * W;
-      const int hi = ho + kh - 1, wi = wo + kw - 1;
-      if ((unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W)
-        acc = fmaf(__ldg(x + ((size_t)(n * 3 + ci) * H + hi) * W + wi), __ldg(dz + (size_t)m * 20 + co), acc);
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int mb = m0; mb < m1; mb += 4) {
+      float xv[4], gv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {      // four independent load pairs in flight
+        const int m = mb + u;
+        xv[u] = 0.f;
+        gv[u] = 0.f;
+        if (m < m1) {
+          const int n = m / hw, rem = m - n * hw;
+          const int ho = rem / W, wo = rem - ho * W;
+          const int hi = ho + kh - 1, wi = wo + kw - 1;
+          if ((unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W) {
+            xv[u] = __ldg(x + ((size_t)(n * 3 + ci) * H + hi) * W + wi);
+            gv[u] = __ldg(dz + (size_t)m * 20 + co);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a4[u] = fmaf(xv[u], gv[u], a4[u]);
     }
+    acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
     part[(size_t)blockIdx.x * 540 + k * 20 + co] = acc;
   }
 }
@@ -522,7 +555,8 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     a.M = N * c.hout * c.wout;
     a.k_total = g.k_total; a.k4_groups = g.k4_groups; a.kw = g.kw; a.nw = g.nw;
     a.pix_per_split = g.pix_per_split;
-    const size_t smem = (size_t)WG_MC * (g.kw * 128 + g.nw * 20) * sizeof(float) + 3 * WG_MC * sizeof(int);
+    const size_t smem = (size_t)WG_NST * WG_MC * (g.kw * 128 + g.nw * 20) * sizeof(float) +
+                        (size_t)(WG_NST + 1) * 3 * WG_MC * sizeof(int);
     static bool configured = false;
     if (!configured) {
       B200OCL_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
