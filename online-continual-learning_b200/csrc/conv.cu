@@ -537,6 +537,7 @@ int launch_conv_ksplit(const ConvArgs& a, cudaStream_t stream) {
 // data gradient (correlation with the spatially flipped taps of the [tap][cout][cin] weights).
 template <int BN, int PT>
 __global__ void __launch_bounds__(CONV_THREADS, (PT <= 2 ? 3 : 2)) conv_patch_kernel(ConvArgs a) {
+  static_assert(PT == 1 || PT == 2 || PT == 4, "pixels per thread");
   constexpr int WN = BN / 20;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(16) double scratch[4 * 20 * 2 * 2];
@@ -696,16 +697,21 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   // Forward convolutions and stride-1 data gradients with enough pixels go to the patch kernel:
   // pick the widest channel tile and 2 pixels per thread that still give >= 3 CTAs per SM.
   if (!a.transposed && a.ks * a.ks * 20 * 80 * sizeof(float) <= 64 * 1024) {
+    // The inner loop issues 5 broadcast LDS.128 (20 weights) per k for 20*PT FMAs and a warp-wide
+    // LDS.128 occupies the shared-memory pipe for 4 cycles, so PT = 2 is shared-memory bound by ~2x
+    // (measured: 22 TFLOP/s); PT = 4 is close to balance.  Take PT = 4 whenever it still fills the SMs.
     const long want3 = 5L * sm_count() / 2;
     const int pbn[3] = {80, 40, 20};
-    const int ppt[2] = {2, 1};
-    for (int pi = 0; pi < 2; ++pi)
+    const int ppt[3] = {4, 2, 1};
+    for (int pi = 0; pi < 3; ++pi)
       for (int bi = 0; bi < 3; ++bi) {
         if (a.CN % pbn[bi]) continue;
         const PatchTile t = patch_tile(a, pbn[bi], ppt[pi]);
-        if (t.ctas < want3 || t.smem > 72 * 1024) continue;
+        const long need = (ppt[pi] == 4) ? 3L * sm_count() / 2 : want3;
+        if (t.ctas < need || t.smem > (ppt[pi] == 4 ? 100 : 72) * 1024) continue;
 #define B200OCL_PATCH_CASE(BN_, PT_) \
         if (pbn[bi] == BN_ && ppt[pi] == PT_) return launch_conv_patch<BN_, PT_>(a, t, stream)
+        B200OCL_PATCH_CASE(80, 4); B200OCL_PATCH_CASE(40, 4); B200OCL_PATCH_CASE(20, 4);
         B200OCL_PATCH_CASE(80, 2); B200OCL_PATCH_CASE(40, 2); B200OCL_PATCH_CASE(20, 2);
         B200OCL_PATCH_CASE(80, 1); B200OCL_PATCH_CASE(40, 1); B200OCL_PATCH_CASE(20, 1);
 #undef B200OCL_PATCH_CASE
