@@ -694,6 +694,8 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     set_error("launch_conv: channel counts must be multiples of 20 (CK=%d CN=%d M=%d)", a.CK, a.CN, a.M);
     return B200OCL_EUNSUPPORTED;
   }
+  // 3x3 stride-1 convolutions with enough 128-pixel tiles run on the tensor cores (conv_tc.cu).
+  if (conv_tc_eligible(a)) return launch_conv_tc(a, stream);
   // Forward convolutions and stride-1 data gradients with enough pixels go to the patch kernel:
   // pick the widest channel tile and 2 pixels per thread that still give >= 3 CTAs per SM.
   if (!a.transposed && a.ks * a.ks * 20 * 80 * sizeof(float) <= 64 * 1024) {

@@ -20,6 +20,8 @@ struct ConvArgs {
   int ks, stride, pad;
   int transposed;    // 0: forward gather (hi = ho*stride - pad + kh); 1: data-gradient gather
                      //    (input pixel (t/stride) with t = ho + pad - kh, only when divisible)
+  const float* w_tc; // tensor-core operand image of the same weights (net_plan.cuh), nullable
+  int tc_kb, tc_bn;  // its K blocks and real channels per tile
   int flip;          // patch kernel only: use tap (ks*ks-1-tap) of the weights (stride-1 data gradient)
   int th, tw, ti;    // patch kernel only: spatial tile (rows, cols, images), set by the launcher
   int M;             // N*Hout*Wout output pixels
@@ -45,6 +47,8 @@ struct ConvArgs {
 // Upper bound of gridDim.x over every tiling launch_conv may choose (sizes stat_part).
 int conv_max_grid_m(int M);
 int launch_conv(const ConvArgs& a, cudaStream_t stream);   // CK, CN multiples of 20
-int launch_stem(const ConvArgs& a, cudaStream_t stream);   // CK == 3, CN == 20, ks == 3, NCHW input
+int launch_stem(const ConvArgs& a, cudaStream_t stream);
+int launch_conv_tc(const ConvArgs& a, cudaStream_t stream);  // conv_tc.cu: tcgen05 3xTF32 path
+bool conv_tc_eligible(const ConvArgs& a);   // CK == 3, CN == 20, ks == 3, NCHW input
 
 }  // namespace b200ocl

@@ -583,6 +583,11 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
       // dx[h,w] = sum_taps dz[h+1-kh, w+1-kw] W[kh,kw]: a forward-style correlation with flipped taps
       a.transposed = 0;
       a.flip = 1;
+      if (c.tc_kb_d) {
+        a.w_tc = st->packed + c.tc_d_off;
+        a.tc_kb = c.tc_kb_d;
+        a.tc_bn = c.tc_bn_d;
+      }
     } else {
       a.transposed = 1;
     }

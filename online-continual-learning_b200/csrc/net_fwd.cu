@@ -8,6 +8,7 @@
 #include <math.h>
 
 #include "net_ws.cuh"
+#include "umma.cuh"
 
 namespace b200ocl {
 namespace {
@@ -35,6 +36,55 @@ __global__ void __launch_bounds__(256) pack_kernel(PackTable t, const float* __r
   }
 }
 
+
+// Tensor-core operand images: B[n][k] tiles, split into TF32 hi / lo, 128-byte swizzled.
+//   forward        n = cout, k = tap*cin + ci            value W[co][ci][tap]
+//   data gradient  n = cin,  k = tap*cout + co (flipped)  value W[co][ci][8 - tap]
+struct TcPackTable {
+  int n;
+  struct {
+    unsigned int w_off, img_off;
+    int cin, cout, bn, nt, kb, dgrad;
+  } e[2 * NET_MAX_CONV];
+};
+
+__global__ void __launch_bounds__(256) tc_pack_kernel(TcPackTable t, const float* __restrict__ params,
+                                                      float* __restrict__ packed) {
+  const auto& L = t.e[blockIdx.y];
+  const int n_ch = L.dgrad ? L.cin : L.cout;      // output channels of this direction
+  const int k_ch = L.dgrad ? L.cout : L.cin;      // channels contracted per tap
+  const int ktot = 9 * k_ch;
+  const int n_tiles = n_ch / L.bn;
+  const int total = n_tiles * L.kb * L.nt * 8;    // (tile, kb, row, 16-byte chunk)
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int c = e & 7;
+    int r = e >> 3;
+    const int row = r % L.nt;
+    r /= L.nt;
+    const int kb = r % L.kb, tile = r / L.kb;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const int k0 = kb * 32 + c * 4;
+    if (row < L.bn && k0 < ktot) {
+      const int tap = k0 / k_ch, kc = k0 - tap * k_ch;   // 4 consecutive k share the tap (k_ch % 4 == 0)
+      const int nch = tile * L.bn + row;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int co = L.dgrad ? kc + j : nch;
+        const int ci = L.dgrad ? nch : kc + j;
+        const int wt = L.dgrad ? 8 - tap : tap;
+        v[j] = params[L.w_off + ((size_t)co * L.cin + ci) * 9 + wt];
+      }
+    }
+    float4 h, l;
+    umma::split_tf32(v[0], h.x, l.x); umma::split_tf32(v[1], h.y, l.y);
+    umma::split_tf32(v[2], h.z, l.z); umma::split_tf32(v[3], h.w, l.w);
+    float* base = packed + L.img_off + ((size_t)(tile * L.kb + kb) * 2) * L.nt * 32;
+    const int off = umma::sw128_offset_f32(row, c);
+    *reinterpret_cast<float4*>(base + off) = h;
+    *reinterpret_cast<float4*>(base + L.nt * 32 + off) = l;
+  }
+}
+
 int launch_pack(const NetPlan& p, const float* params, float* packed, cudaStream_t stream) {
   PackTable t{};
   t.n = p.n_conv;
@@ -49,6 +99,26 @@ int launch_pack(const NetPlan& p, const float* params, float* packed, cudaStream
   B200OCL_PROF("pack", 12.0 * p.n_packed / 2, stream);
   pack_kernel<<<dim3(16, p.n_conv), 256, 0, stream>>>(t, params, packed);
   B200OCL_LAUNCHED();
+  TcPackTable tc{};
+  for (int i = 0; i < p.n_conv; ++i) {
+    const ConvL& c = p.conv[i];
+    if (!c.tc_kb_f) continue;
+    for (int d = 0; d < 2; ++d) {
+      auto& e = tc.e[tc.n++];
+      e.w_off = (unsigned)c.w_off;
+      e.img_off = (unsigned)(d ? c.tc_d_off : c.tc_f_off);
+      e.cin = c.cin; e.cout = c.cout;
+      e.bn = d ? c.tc_bn_d : c.tc_bn_f;
+      e.nt = tc_nt(e.bn);
+      e.kb = d ? c.tc_kb_d : c.tc_kb_f;
+      e.dgrad = d;
+    }
+  }
+  if (tc.n) {
+    B200OCL_PROF("pack", 16.0 * p.n_packed / 2, stream);
+    tc_pack_kernel<<<dim3(32, tc.n), 256, 0, stream>>>(tc, params, packed);
+    B200OCL_LAUNCHED();
+  }
   return B200OCL_OK;
 }
 
@@ -267,6 +337,11 @@ void fill_conv_common(ConvArgs& a, const ConvL& c, int N, const float* in, const
   a.M = N * c.hout * c.wout;
   a.eps = NET_BN_EPS;
   a.momentum = NET_BN_MOMENTUM;
+  if (c.tc_kb_f) {
+    a.w_tc = packed + c.tc_f_off;
+    a.tc_kb = c.tc_kb_f;
+    a.tc_bn = c.tc_bn_f;
+  }
 }
 
 int conv_eval(const NetPlan& p, const b200ocl_net_state& st, int ci, int N, const float* in, float* out,

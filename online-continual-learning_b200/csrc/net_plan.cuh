@@ -27,7 +27,15 @@ struct ConvL {
   size_t pkf_off;   // packed forward weight   [ks*ks][cin][cout]
   size_t pkd_off;   // packed data-grad weight [ks*ks][cout][cin]
   size_t act_off;   // per-image offset of this conv's output inside an activation slab (floats)
+  // tensor-core operand images (3x3 stride-1 convolutions only; tc_kb_f == 0 otherwise):
+  //   [channel tile][K block of 32][hi | lo][NT rows x 32 fp32, 128-byte swizzle] -- byte-copyable into smem
+  size_t tc_f_off, tc_d_off;  // forward / flipped data-gradient image in the packed arena
+  int tc_kb_f, tc_kb_d;       // K blocks: ceil(9*cin/32), ceil(9*cout/32)
+  int tc_bn_f, tc_bn_d;       // real channels per tile: min(cout,80) / min(cin,80)
 };
+
+// padded MMA N for a channel tile of 20 / 40 / 80 channels (tcgen05 M=128 needs N % 16 == 0)
+inline int tc_nt(int bn) { return bn <= 20 ? 32 : (bn <= 40 ? 48 : 80); }
 struct BnL {
   int c;
   size_t g_off, b_off;  // gamma / beta in the parameter arena
@@ -82,6 +90,14 @@ inline int build_plan(const b200ocl_net_desc& d, NetPlan& p) {
     c.pkf_off = pk; pk += (size_t)cout * cin * ks * ks;
     c.pkd_off = pk; pk += (size_t)cout * cin * ks * ks;
     c.act_off = act;
+    if (ks == 3 && stride == 1 && cin % 20 == 0) {
+      c.tc_bn_f = cout < 80 ? cout : 80;
+      c.tc_bn_d = cin < 80 ? cin : 80;
+      c.tc_kb_f = (9 * cin + 31) / 32;
+      c.tc_kb_d = (9 * cout + 31) / 32;
+      c.tc_f_off = pk; pk += (size_t)(cout / c.tc_bn_f) * c.tc_kb_f * 2 * tc_nt(c.tc_bn_f) * 32;
+      c.tc_d_off = pk; pk += (size_t)(cin / c.tc_bn_d) * c.tc_kb_d * 2 * tc_nt(c.tc_bn_d) * 32;
+    }
     const size_t a = (size_t)c.hout * c.wout * cout;
     act += a;
     if (a > max_act) max_act = a;
