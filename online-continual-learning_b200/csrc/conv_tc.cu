@@ -285,6 +285,292 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(ConvArgs a) {
   if (warp == 0) umma::tmem_dealloc(tmem, TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Warp-specialised version (default).  The v1 kernel above runs gather -> MMA -> promote in lockstep
+// and measured ~4400 cycles per K block with the tensor pipe ~10 % busy; here the three roles run
+// concurrently through mbarrier rings:
+//   warps 0-3  producers  thread = pixel row; next block's 8 x LDG.128 are in flight while the
+//                         current block is split and stored; B image copied alongside; arrive full[s]
+//   warp  8    MMA issue  one thread: wait full[s] and tmem_empty[t], 12 x tcgen05.mma, commit ->
+//                         empty[s] (smem stage reusable) and tmem_full[t]
+//   warps 4-7  promote    wait tmem_full[t], tcgen05.ld their 32 lanes, add into fp32 registers,
+//                         arrive tmem_empty[t]; then run the epilogue
+template <int NT>
+__global__ void __launch_bounds__(288) conv_tc_ws_kernel(ConvArgs a) {
+  constexpr int B_TILE = NT * 32;
+  constexpr int STAGE_F = 2 * A_TILE + 2 * B_TILE;
+  constexpr int S = 3;
+  constexpr uint32_t TMEM_COLS = (2 * NT <= 64) ? 64 : ((2 * NT <= 128) ? 128 : 256);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* stage0 = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ bool is_last;
+  __shared__ int s_fail;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int bn = a.tc_bn;
+  const int n0 = blockIdx.y * bn;
+  const int KB = a.tc_kb;
+
+  if (warp == 8) umma::tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) {
+      umma::mbar_init(&full_bar[i], 128);
+      umma::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(&tfull_bar[i], 1);
+      umma::mbar_init(&tempty_bar[i], 128);
+    }
+    umma::fence_mbar_init();
+    s_fail = 0;
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    // =========================================================== producers
+    const int m = blockIdx.x * 128 + tid;
+    const bool valid = m < a.M;
+    const int hw = a.Hout * a.Wout;
+    const int img = valid ? m / hw : 0;
+    const int rem = valid ? m - img * hw : 0;
+    const int py = rem / a.Wout, px = rem - py * a.Wout;
+    const float* wimg = a.w_tc + (size_t)blockIdx.y * KB * 2 * B_TILE;
+    int tap = 0, ci = 0;
+    const float* tap_src = nullptr;
+    auto set_tap = [&]() {
+      const int kh = tap / 3, kw = tap - kh * 3;
+      const int iy = py + kh - 1, ix = px + kw - 1;
+      const bool ok = valid && tap < 9 && (unsigned)iy < (unsigned)a.Hin && (unsigned)ix < (unsigned)a.Win;
+      tap_src = ok ? a.in + ((size_t)(img * a.Hin + iy) * a.Win + ix) * a.CK : nullptr;
+    };
+    auto load_block = [&](float4 (&v)[8]) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tap_src != nullptr) v[c] = __ldg(reinterpret_cast<const float4*>(tap_src + ci));
+        ci += 4;
+        if (ci == a.CK) {
+          ci = 0;
+          ++tap;
+          set_tap();
+        }
+      }
+    };
+    set_tap();
+    float4 va[8], vb[8];
+    load_block(va);
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % S;
+      // prefetch the next block's activations before touching the current one
+      if (kb + 1 < KB) {
+        if (kb & 1) load_block(va); else load_block(vb);
+      }
+      if (!umma::mbar_wait(&empty_bar[s], (uint32_t)(((kb / S) & 1) ^ 1))) s_fail = 1;
+      float* sAh = stage0 + s * STAGE_F;
+      float* sAl = sAh + A_TILE;
+      float* sB = sAl + A_TILE;
+      const float4* bsrc = reinterpret_cast<const float4*>(wimg + (size_t)kb * 2 * B_TILE);
+      float4 bw[(2 * B_TILE / 4) / 128];
+#pragma unroll
+      for (int i = 0; i < (2 * B_TILE / 4) / 128; ++i) bw[i] = __ldg(bsrc + tid + i * 128);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 x = (kb & 1) ? vb[c] : va[c];
+        float4 h, l;
+        umma::split_tf32(x.x, h.x, l.x); umma::split_tf32(x.y, h.y, l.y);
+        umma::split_tf32(x.z, h.z, l.z); umma::split_tf32(x.w, h.w, l.w);
+        const int off = umma::sw128_offset_f32(tid, c);
+        *reinterpret_cast<float4*>(sAh + off) = h;
+        *reinterpret_cast<float4*>(sAl + off) = l;
+      }
+#pragma unroll
+      for (int i = 0; i < (2 * B_TILE / 4) / 128; ++i) reinterpret_cast<float4*>(sB)[tid + i * 128] = bw[i];
+      umma::fence_proxy_async_smem();
+      umma::mbar_arrive(&full_bar[s]);
+    }
+  } else if (warp == 8) {
+    // =========================================================== MMA issuer
+    if ((tid & 31) == 0) {
+      const uint32_t idesc = umma::make_idesc_tf32(128, NT);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % S, t = kb & 1;
+        if (!umma::mbar_wait(&full_bar[s], (uint32_t)((kb / S) & 1))) s_fail = 1;
+        if (!umma::mbar_wait(&tempty_bar[t], (uint32_t)(((kb >> 1) & 1) ^ 1))) s_fail = 1;
+        umma::fence_after_thread_sync();
+        float* sAh = stage0 + s * STAGE_F;
+        const uint64_t dAh = umma::make_smem_desc_sw128(umma::smem_u32(sAh));
+        const uint64_t dAl = umma::make_smem_desc_sw128(umma::smem_u32(sAh + A_TILE));
+        const uint64_t dBh = umma::make_smem_desc_sw128(umma::smem_u32(sAh + 2 * A_TILE));
+        const uint64_t dBl = umma::make_smem_desc_sw128(umma::smem_u32(sAh + 2 * A_TILE + B_TILE));
+        const uint32_t dcol = tmem + (uint32_t)(t * NT);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t adv = (uint64_t)(k * 2);
+          umma::mma_tf32_ss(dcol, dAh + adv, dBh + adv, idesc, k > 0 ? 1u : 0u);
+          umma::mma_tf32_ss(dcol, dAh + adv, dBl + adv, idesc, 1u);
+          umma::mma_tf32_ss(dcol, dAl + adv, dBh + adv, idesc, 1u);
+        }
+        umma::mma_commit(&empty_bar[s]);
+        umma::mma_commit(&tfull_bar[t]);
+      }
+    }
+  } else {
+    // =========================================================== promotion + epilogue (warps 4-7)
+    const int et = tid - 128;                 // 0..127 = pixel row = TMEM lane
+    const int ew = warp - 4;                  // == warp % 4: the TMEM lane quarter this warp may read
+    const uint32_t my_lanes = tmem + ((uint32_t)(ew * 32) << 16);
+    const int m = blockIdx.x * 128 + et;
+    const bool valid = m < a.M;
+    float acc[NT];
+#pragma unroll
+    for (int c = 0; c < NT; ++c) acc[c] = 0.f;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int t = kb & 1;
+      if (!umma::mbar_wait(&tfull_bar[t], (uint32_t)((kb >> 1) & 1))) s_fail = 1;
+      umma::fence_after_thread_sync();
+      tmem_accumulate<NT>(my_lanes + (uint32_t)(t * NT), acc);
+      umma::fence_before_thread_sync();
+      umma::mbar_arrive(&tempty_bar[t]);
+    }
+    // ---- epilogue: identical arithmetic to the v1 kernel; barriers are the named barrier 1 (128 threads)
+    auto esync = []() { asm volatile("bar.sync 1, 128;\n" ::); };
+    if (a.mode == CONV_EVAL) {
+      if (valid) {
+        float* o = a.out + (size_t)m * a.CN + n0;
+        const float* rs = a.residual ? a.residual + (size_t)m * a.CN + n0 : nullptr;
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 4) {
+          if (c0 >= bn) break;
+          float r[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = n0 + c0 + j;
+            const float inv = 1.0f / sqrtf(a.rvar[c] + a.eps);
+            r[j] = (acc[c0 + j] - a.rmean[c]) * (inv * a.gamma[c]) + a.beta[c];
+          }
+          if (rs) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rs + c0);
+            r[0] += r4.x; r[1] += r4.y; r[2] += r4.z; r[3] += r4.w;
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = fmaxf(r[j], 0.f);
+          }
+          *reinterpret_cast<float4*>(o + c0) = make_float4(r[0], r[1], r[2], r[3]);
+        }
+      }
+    } else {
+      if (valid) {
+        float* o = a.out + (size_t)m * a.CN + n0;
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 4) {
+          if (c0 >= bn) break;
+          float4 r = make_float4(acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]);
+          if (a.mode == CONV_ACCUM) {
+            const float4 old = *reinterpret_cast<const float4*>(o + c0);
+            r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+          }
+          *reinterpret_cast<float4*>(o + c0) = r;
+        }
+      }
+      if (a.mode == CONV_TRAIN) {
+        // every MMA has completed (the last tfull was consumed), so the staging ring is free
+        float* s_t = stage0;  // [128][bn + 1]
+#pragma unroll
+        for (int c = 0; c < NT; ++c)
+          if (c < bn) s_t[et * (bn + 1) + c] = acc[c];
+        esync();
+        if (et < bn) {
+          double Sm = 0.0, Q = 0.0;
+          for (int r = 0; r < 128; ++r) {
+            const double x = (double)s_t[r * (bn + 1) + et];
+            Sm += x;
+            Q += x * x;
+          }
+          double* dst = a.stat_part + ((size_t)blockIdx.x * a.CN + n0 + et) * 2;
+          dst[0] = Sm;
+          dst[1] = Q;
+        }
+        __threadfence();
+        esync();
+        if (et == 0) is_last = (atomicAdd(a.counter + blockIdx.y, 1u) == gridDim.x - 1);
+        esync();
+        if (is_last) {
+          __threadfence();
+          const int groups = 128 / bn;
+          const int ch = et % bn, grp = et / bn;
+          double* s_fin = reinterpret_cast<double*>(stage0);
+          esync();
+          if (grp < groups) {
+            double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};
+            unsigned int b = grp;
+            for (; b + 3 * groups < gridDim.x; b += 4 * groups) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const double2 pv = __ldcg(reinterpret_cast<const double2*>(a.stat_part + ((size_t)(b + u * groups) * a.CN + n0 + ch) * 2));
+                s4[u] += pv.x;
+                q4[u] += pv.y;
+              }
+            }
+            for (; b < gridDim.x; b += groups) {
+              const double2 pv = __ldcg(reinterpret_cast<const double2*>(a.stat_part + ((size_t)b * a.CN + n0 + ch) * 2));
+              s4[0] += pv.x;
+              q4[0] += pv.y;
+            }
+            s_fin[(grp * bn + ch) * 2 + 0] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            s_fin[(grp * bn + ch) * 2 + 1] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+          }
+          esync();
+          if (et < bn) {
+            double Sm = 0.0, Q = 0.0;
+            for (int g = 0; g < groups; ++g) {
+              Sm += s_fin[(g * bn + et) * 2 + 0];
+              Q += s_fin[(g * bn + et) * 2 + 1];
+            }
+            const double cnt = (double)a.M;
+            const double mean = Sm / cnt;
+            double var = Q / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const int c = n0 + et;
+            a.save_mean[c] = (float)mean;
+            a.save_invstd[c] = (float)(1.0 / sqrt(var + (double)a.eps));
+            const double unbiased = (a.M > 1) ? var * cnt / (cnt - 1.0) : var;
+            a.run_mean[c] = (1.f - a.momentum) * a.run_mean[c] + a.momentum * (float)mean;
+            a.run_var[c] = (1.f - a.momentum) * a.run_var[c] + a.momentum * (float)unbiased;
+          }
+        }
+      }
+    }
+    esync();
+    if (s_fail && valid) a.out[(size_t)m * a.CN + n0] = __int_as_float(0x7fc00000);
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 8) umma::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int NT>
+int launch_tc_ws(const ConvArgs& a, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)3 * (2 * A_TILE + 2 * NT * 32) * sizeof(float) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200OCL_CUDA(cudaFuncSetAttribute(conv_tc_ws_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((a.M + 127) / 128, a.CN / a.tc_bn);
+  B200OCL_PROF(a.flip ? "conv_tc_dgrad" : (a.mode == CONV_EVAL ? "conv_tc_eval" : "conv_tc_train"),
+               2.0 * a.M * (double)a.CN * a.CK * 9.0, stream);
+  conv_tc_ws_kernel<NT><<<grid, 288, smem, stream>>>(a);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
+
 template <int NT>
 int launch_tc(const ConvArgs& a, cudaStream_t stream) {
   constexpr size_t smem = (size_t)2 * (2 * A_TILE + 2 * NT * 32) * sizeof(float) + 1024;
@@ -317,10 +603,20 @@ bool conv_tc_eligible(const ConvArgs& a) {
 }
 
 int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
+  static int version = 0;
+  if (!version) {
+    const char* e = getenv("B200OCL_TC");
+    version = (e && e[0] == '1') ? 1 : 2;      // B200OCL_TC=1: lockstep kernel, default: warp-specialised
+  }
   const int nt = a.tc_bn <= 20 ? 32 : (a.tc_bn <= 40 ? 48 : 80);
-  if (nt == 32) return launch_tc<32>(a, stream);
-  if (nt == 48) return launch_tc<48>(a, stream);
-  return launch_tc<80>(a, stream);
+  if (version == 1) {
+    if (nt == 32) return launch_tc<32>(a, stream);
+    if (nt == 48) return launch_tc<48>(a, stream);
+    return launch_tc<80>(a, stream);
+  }
+  if (nt == 32) return launch_tc_ws<32>(a, stream);
+  if (nt == 48) return launch_tc_ws<48>(a, stream);
+  return launch_tc_ws<80>(a, stream);
 }
 
 }  // namespace b200ocl
