@@ -290,14 +290,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(ConvArgs a) {
 // Warp-specialised version (default).  The v1 kernel above runs gather -> MMA -> promote in lockstep
 // and measured ~4400 cycles per K block with the tensor pipe ~10 % busy; here the three roles run
 // concurrently through mbarrier rings:
-//   warps 0-3  producers  thread = pixel row; next block's 8 x LDG.128 are in flight while the
-//                         current block is split and stored; B image copied alongside; arrive full[s]
-//   warp  8    MMA issue  one thread: wait full[s] and tmem_empty[t], 12 x tcgen05.mma, commit ->
-//                         empty[s] (smem stage reusable) and tmem_full[t]
-//   warps 4-7  promote    wait tmem_full[t], tcgen05.ld their 32 lanes, add into fp32 registers,
-//                         arrive tmem_empty[t]; then run the epilogue
+//   warps 0-7   producers  two threads per pixel row (4 of its 8 chunks each): a lone warp per scheduler
+//                          runs the convert/store chain at IPC ~0.3, so the staging work is spread over
+//                          8 warps; the next block's LDG.128s are in flight while the current block is
+//                          split (cvt.rna.tf32) and stored; B image copied alongside; arrive full[s]
+//   warp  12    MMA issue  one thread: wait full[s] and tmem_empty[t], 12 x tcgen05.mma, commit ->
+//                          empty[s] (smem stage reusable) and tmem_full[t]
+//   warps 8-11  promote    wait tmem_full[t], tcgen05.ld their 32 lanes, add into fp32 registers,
+//                          arrive tmem_empty[t]; then run the epilogue
 template <int NT>
-__global__ void __launch_bounds__(288) conv_tc_ws_kernel(ConvArgs a) {
+__global__ void __launch_bounds__(416) conv_tc_ws_kernel(ConvArgs a) {
   constexpr int B_TILE = NT * 32;
   constexpr int STAGE_F = 2 * A_TILE + 2 * B_TILE;
   constexpr int S = 3;
@@ -314,10 +316,10 @@ __global__ void __launch_bounds__(288) conv_tc_ws_kernel(ConvArgs a) {
   const int n0 = blockIdx.y * bn;
   const int KB = a.tc_kb;
 
-  if (warp == 8) umma::tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (warp == 12) umma::tmem_alloc(&tmem_slot, TMEM_COLS);
   if (tid == 0) {
     for (int i = 0; i < S; ++i) {
-      umma::mbar_init(&full_bar[i], 128);
+      umma::mbar_init(&full_bar[i], 256);
       umma::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -332,9 +334,10 @@ __global__ void __launch_bounds__(288) conv_tc_ws_kernel(ConvArgs a) {
   umma::fence_after_thread_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =========================================================== producers
-    const int m = blockIdx.x * 128 + tid;
+    const int row = tid & 127, half = tid >> 7;      // this thread stages chunks [4*half, 4*half+4) of its row
+    const int m = blockIdx.x * 128 + row;
     const bool valid = m < a.M;
     const int hw = a.Hout * a.Wout;
     const int img = valid ? m / hw : 0;
@@ -349,52 +352,61 @@ __global__ void __launch_bounds__(288) conv_tc_ws_kernel(ConvArgs a) {
       const bool ok = valid && tap < 9 && (unsigned)iy < (unsigned)a.Hin && (unsigned)ix < (unsigned)a.Win;
       tap_src = ok ? a.in + ((size_t)(img * a.Hin + iy) * a.Win + ix) * a.CK : nullptr;
     };
-    auto load_block = [&](float4 (&v)[8]) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tap_src != nullptr) v[c] = __ldg(reinterpret_cast<const float4*>(tap_src + ci));
-        ci += 4;
-        if (ci == a.CK) {
-          ci = 0;
-          ++tap;
-          set_tap();
-        }
+    auto advance = [&]() {   // one 16-byte chunk further along (tap, channel)
+      ci += 4;
+      if (ci == a.CK) {
+        ci = 0;
+        ++tap;
+        set_tap();
       }
     };
+    auto load_block = [&](float4 (&v)[4]) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tap_src != nullptr) v[c] = __ldg(reinterpret_cast<const float4*>(tap_src + ci));
+        advance();
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) advance();   // the partner thread's chunks
+    };
     set_tap();
-    float4 va[8], vb[8];
+    if (half) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) advance();
+    }
+    float4 va[4], vb[4];
     load_block(va);
+    constexpr int BW = (2 * B_TILE / 4) / 256;
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % S;
-      // prefetch the next block's activations before touching the current one
-      if (kb + 1 < KB) {
+      if (kb + 1 < KB) {   // prefetch the next block's activations before touching the current one
         if (kb & 1) load_block(va); else load_block(vb);
       }
+      const float4* bsrc = reinterpret_cast<const float4*>(wimg + (size_t)kb * 2 * B_TILE);
+      float4 bw[BW];
+#pragma unroll
+      for (int i = 0; i < BW; ++i) bw[i] = __ldg(bsrc + tid + i * 256);
       if (!umma::mbar_wait(&empty_bar[s], (uint32_t)(((kb / S) & 1) ^ 1))) s_fail = 1;
       float* sAh = stage0 + s * STAGE_F;
       float* sAl = sAh + A_TILE;
       float* sB = sAl + A_TILE;
-      const float4* bsrc = reinterpret_cast<const float4*>(wimg + (size_t)kb * 2 * B_TILE);
-      float4 bw[(2 * B_TILE / 4) / 128];
 #pragma unroll
-      for (int i = 0; i < (2 * B_TILE / 4) / 128; ++i) bw[i] = __ldg(bsrc + tid + i * 128);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         const float4 x = (kb & 1) ? vb[c] : va[c];
         float4 h, l;
         umma::split_tf32(x.x, h.x, l.x); umma::split_tf32(x.y, h.y, l.y);
         umma::split_tf32(x.z, h.z, l.z); umma::split_tf32(x.w, h.w, l.w);
-        const int off = umma::sw128_offset_f32(tid, c);
+        const int off = umma::sw128_offset_f32(row, half * 4 + c);
         *reinterpret_cast<float4*>(sAh + off) = h;
         *reinterpret_cast<float4*>(sAl + off) = l;
       }
 #pragma unroll
-      for (int i = 0; i < (2 * B_TILE / 4) / 128; ++i) reinterpret_cast<float4*>(sB)[tid + i * 128] = bw[i];
+      for (int i = 0; i < BW; ++i) reinterpret_cast<float4*>(sB)[tid + i * 256] = bw[i];
       umma::fence_proxy_async_smem();
       umma::mbar_arrive(&full_bar[s]);
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // =========================================================== MMA issuer
     if ((tid & 31) == 0) {
       const uint32_t idesc = umma::make_idesc_tf32(128, NT);
@@ -421,9 +433,9 @@ __global__ void __launch_bounds__(288) conv_tc_ws_kernel(ConvArgs a) {
       }
     }
   } else {
-    // =========================================================== promotion + epilogue (warps 4-7)
-    const int et = tid - 128;                 // 0..127 = pixel row = TMEM lane
-    const int ew = warp - 4;                  // == warp % 4: the TMEM lane quarter this warp may read
+    // =========================================================== promotion + epilogue (warps 8-11)
+    const int et = tid - 256;                 // 0..127 = pixel row = TMEM lane
+    const int ew = warp - 8;                  // == warp % 4: the TMEM lane quarter this warp may read
     const uint32_t my_lanes = tmem + ((uint32_t)(ew * 32) << 16);
     const int m = blockIdx.x * 128 + et;
     const bool valid = m < a.M;
@@ -552,7 +564,7 @@ __global__ void __launch_bounds__(288) conv_tc_ws_kernel(ConvArgs a) {
   }
   umma::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 8) umma::tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == 12) umma::tmem_dealloc(tmem, TMEM_COLS);
 }
 
 template <int NT>
@@ -566,7 +578,7 @@ int launch_tc_ws(const ConvArgs& a, cudaStream_t stream) {
   dim3 grid((a.M + 127) / 128, a.CN / a.tc_bn);
   B200OCL_PROF(a.flip ? "conv_tc_dgrad" : (a.mode == CONV_EVAL ? "conv_tc_eval" : "conv_tc_train"),
                2.0 * a.M * (double)a.CN * a.CK * 9.0, stream);
-  conv_tc_ws_kernel<NT><<<grid, 288, smem, stream>>>(a);
+  conv_tc_ws_kernel<NT><<<grid, 416, smem, stream>>>(a);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
 }
@@ -606,7 +618,11 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
   static int version = 0;
   if (!version) {
     const char* e = getenv("B200OCL_TC");
-    version = (e && e[0] == '1') ? 1 : 2;      // B200OCL_TC=1: lockstep kernel, default: warp-specialised
+    // B200OCL_TC=2: warp-specialised kernel; default: lockstep kernel (2 CTAs / SM).  Measured on B200 both
+    // are bound by the tensor-core instruction stream, not by staging: a tcgen05.mma.kind::tf32 with N <= 80
+    // costs ~170 cycles however small the tile, and a 128-pixel tile of a 20-channel layer needs 72 of them
+    // (24 K steps x 3 split products); the lockstep kernel is the faster of the two by ~15 %.
+    version = (e && e[0] == '2') ? 2 : 1;
   }
   const int nt = a.tc_bn <= 20 ? 32 : (a.tc_bn <= 40 ? 48 : 80);
   if (version == 1) {

@@ -44,10 +44,11 @@ inline WgradCfg wgrad_cfg(const ConvL& c, int N, int sms) {
   g.grid_k = (k_tiles + g.kw - 1) / g.kw;
   g.grid_n = (n_groups + g.nw - 1) / g.nw;
   const int M = N * c.hout * c.wout;
-  // ~4 CTAs per SM overall, at least 128 pixels of reduction per CTA (every split costs a
-  // K x Cout partial that the finalize kernel has to read back)
-  int splits = (4 * sms + g.grid_k * g.grid_n - 1) / (g.grid_k * g.grid_n);
-  const int max_by_pixels = (M + 127) / 128;
+  // >= 16 resident warps per SM overall, at least 64 pixels of reduction per CTA (fewer, larger splits
+  // measured slower: the kernel needs the parallelism more than the finalize pass needs fewer partials)
+  const int warps_per_cta = g.kw * g.nw;
+  int splits = (16 * sms + warps_per_cta * g.grid_k * g.grid_n - 1) / (warps_per_cta * g.grid_k * g.grid_n);
+  const int max_by_pixels = (M + 63) / 64;
   if (splits > max_by_pixels) splits = max_by_pixels;
   if (splits < 1) splits = 1;
   g.pix_per_split = ((M + splits - 1) / splits + 15) / 16 * 16;

@@ -124,17 +124,19 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// ---- TF32 split: x ~= hi + lo, both exactly representable in TF32 (10 explicit mantissa bits) so the
-// tensor core's operand truncation is a no-op.  hi is x ROUNDED to nearest (a truncated hi leaves a
-// same-signed remainder whose own truncation error then accumulates linearly over K -- measured 1e-5
-// relative at K = 736 on ReLU inputs); lo is the rounded remainder.  |x - hi - lo| <= 2^-22 |x|, unbiased.
+// ---- TF32 split: x = hi + lo with hi = x ROUNDED to TF32 (cvt.rna: one instruction) and lo the exact
+// fp32 remainder.  Rounding matters: a truncated hi leaves a same-signed remainder whose own truncation
+// by the tensor core then accumulates linearly over K (measured 1e-5 relative at K = 736 on ReLU inputs).
+// With a rounded hi the remainder is sign-symmetric, so the hardware's truncation of lo to 10 mantissa
+// bits (|error| <= 2^-22 |x|) is unbiased and needs no second rounding.
 __device__ __forceinline__ float round_tf32(float x) {
-  const uint32_t b = __float_as_uint(x);
-  return __uint_as_float((b + 0x0FFFu + ((b >> 13) & 1u)) & 0xFFFFE000u);
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = round_tf32(x);
-  lo = round_tf32(x - hi);
+  lo = x - hi;
 }
 
 }  // namespace umma
