@@ -378,15 +378,28 @@ __global__ void __launch_bounds__(416) conv_tc_ws_kernel(ConvArgs a) {
     float4 va[4], vb[4];
     load_block(va);
     constexpr int BW = (2 * B_TILE / 4) / 256;
+    // weights of block kb are also fetched one iteration early, so no load is consumed in the
+    // iteration that issued it
+    float4 bwa[BW], bwb[BW];
+    {
+      const float4* bsrc0 = reinterpret_cast<const float4*>(wimg);
+#pragma unroll
+      for (int i = 0; i < BW; ++i) bwa[i] = __ldg(bsrc0 + tid + i * 256);
+    }
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % S;
-      if (kb + 1 < KB) {   // prefetch the next block's activations before touching the current one
-        if (kb & 1) load_block(va); else load_block(vb);
-      }
-      const float4* bsrc = reinterpret_cast<const float4*>(wimg + (size_t)kb * 2 * B_TILE);
-      float4 bw[BW];
+      if (kb + 1 < KB) {   // prefetch the next block's activations and weights before touching the current one
+        const float4* bsrc = reinterpret_cast<const float4*>(wimg + (size_t)(kb + 1) * 2 * B_TILE);
+        if (kb & 1) {
+          load_block(va);
 #pragma unroll
-      for (int i = 0; i < BW; ++i) bw[i] = __ldg(bsrc + tid + i * 256);
+          for (int i = 0; i < BW; ++i) bwa[i] = __ldg(bsrc + tid + i * 256);
+        } else {
+          load_block(vb);
+#pragma unroll
+          for (int i = 0; i < BW; ++i) bwb[i] = __ldg(bsrc + tid + i * 256);
+        }
+      }
       if (!umma::mbar_wait(&empty_bar[s], (uint32_t)(((kb / S) & 1) ^ 1))) s_fail = 1;
       float* sAh = stage0 + s * STAGE_F;
       float* sAl = sAh + A_TILE;
@@ -402,7 +415,7 @@ __global__ void __launch_bounds__(416) conv_tc_ws_kernel(ConvArgs a) {
         *reinterpret_cast<float4*>(sAl + off) = l;
       }
 #pragma unroll
-      for (int i = 0; i < BW; ++i) reinterpret_cast<float4*>(sB)[tid + i * 256] = bw[i];
+      for (int i = 0; i < BW; ++i) reinterpret_cast<float4*>(sB)[tid + i * 256] = (kb & 1) ? bwb[i] : bwa[i];
       umma::fence_proxy_async_smem();
       umma::mbar_arrive(&full_bar[s]);
     }
@@ -618,10 +631,12 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
   static int version = 0;
   if (!version) {
     const char* e = getenv("B200OCL_TC");
-    // B200OCL_TC=2: warp-specialised kernel; default: lockstep kernel (2 CTAs / SM).  Measured on B200 both
-    // are bound by the tensor-core instruction stream, not by staging: a tcgen05.mma.kind::tf32 with N <= 80
-    // costs ~170 cycles however small the tile, and a 128-pixel tile of a 20-channel layer needs 72 of them
-    // (24 K steps x 3 split products); the lockstep kernel is the faster of the two by ~15 %.
+    // B200OCL_TC=2: warp-specialised kernel; default: lockstep kernel (2 CTAs / SM).  Measured on B200
+    // (tools/umma_latency.py, profiles/r01_v3_*): the MMAs themselves are cheap -- 8 extra
+    // tcgen05.mma.kind::tf32 per K block cost ~80 ns at N = 32 (~19 cycles each, the documented floor) and
+    // the tensor pipe is ~10 % active -- what a K block costs is its staging chain (gather, TF32 split,
+    // swizzled stores, proxy fence, barrier: ~2 us single-CTA).  Two lockstep CTAs per SM overlap that chain
+    // better than one warp-specialised CTA does; the lockstep kernel is the faster of the two by ~7 %.
     version = (e && e[0] == '2') ? 2 : 1;
   }
   const int nt = a.tc_bn <= 20 ? 32 : (a.tc_bn <= 40 ? 48 : 80);
