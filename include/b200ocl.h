@@ -187,6 +187,13 @@ int b200ocl_scr_augment(const float* x, float* out, const float* params, int N, 
 int b200ocl_selftest_umma_tf32(const float* A, const float* B, float* D, int N, int K, int mode, int* status,
                                void* stream);
 
+/* Window variant: A is read in place from a larger swizzled buffer P[rows][32] of 128-byte rows (tile row
+ * 8g + r = P row start_row + g * sbo_rows + r), start address unaligned to the swizzle repeat when
+ * start_row % 8 != 0; base_off_mode 1 sets the descriptor's base-offset field to start_row & 7.  Validates the
+ * addressing the halo-patch tensor-core convolution relies on.  D[128,N] = A_window * B[N,32]^T, single TF32 pass. */
+int b200ocl_selftest_umma_window(const float* P, const float* B, float* D, int rows, int start_row, int sbo_rows,
+                                 int base_off_mode, int N, int* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,7 @@ SIGNATURES = {
     'b200ocl_ce_loss': (c_int, [P, P, c_int, c_int, P, P, P, P, P]),
     'b200ocl_scr_augment': (c_int, [P, P, P, c_int, c_int, c_int, P]),
     'b200ocl_selftest_umma_tf32': (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
+    'b200ocl_selftest_umma_window': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
 }
 
 _lib = None

@@ -145,23 +145,20 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, float (&acc)[PT
   const int ch = tid % BN, grp = tid / BN;
   double s = 0.0, q = 0.0;
   if (grp < GROUPS) {
-    double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};
     unsigned int b = grp;
-    for (; b + 3 * GROUPS < gridDim.x; b += 4 * GROUPS) {      // four loads in flight, fixed association
+    for (; b + 7 * GROUPS < gridDim.x; b += 8 * GROUPS) {      // eight loads in flight, fixed association
+      double2 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const double2 v = __ldcg(reinterpret_cast<const double2*>(a.stat_part + ((size_t)(b + u * GROUPS) * a.CN + n0 + ch) * 2));
-        s4[u] += v.x;
-        q4[u] += v.y;
-      }
+      for (int u = 0; u < 8; ++u)
+        v[u] = __ldcg(reinterpret_cast<const double2*>(a.stat_part + ((size_t)(b + u * GROUPS) * a.CN + n0 + ch) * 2));
+      s += ((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x));
+      q += ((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y));
     }
     for (; b < gridDim.x; b += GROUPS) {
       const double2 v = __ldcg(reinterpret_cast<const double2*>(a.stat_part + ((size_t)b * a.CN + n0 + ch) * 2));
-      s4[0] += v.x;
-      q4[0] += v.y;
+      s += v.x;
+      q += v.y;
     }
-    s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-    q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
   }
   __syncthreads();  // s_stat reuse
   double* s_fin = scratch;  // [GROUPS][BN][2]
@@ -361,10 +358,10 @@ __global__ void __launch_bounds__(CONV_THREADS) stem_kernel(ConvArgs a) {
 // (72 chunks for the 160-channel layers).  Here a CTA owns only 32*PT pixels x 20 channels and its
 // four warps each take every fourth (tap, 20-channel) chunk; partial sums meet in shared memory in
 // warp order (deterministic) and warp 0 runs the epilogue.  4x shorter dependency chain, 4-8x more CTAs.
-template <int PT>
-__global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a) {
-  constexpr int BM = 32 * PT, BN = 20, KS = 4;
-  constexpr int NST = (PT == 1) ? 4 : 3;   // cp.async ring depth: the per-iteration math is shorter than one L2 round trip
+template <int PT, int KS>
+__global__ void __launch_bounds__(32 * KS, (KS == 4 ? 4 : 1)) conv_ksplit_kernel(ConvArgs a) {
+  constexpr int BM = 32 * PT, BN = 20, THREADS = 32 * KS;
+  constexpr int NST = (PT == 1 && KS == 4) ? 4 : 3;   // cp.async ring depth: the per-iteration math is shorter than one L2 round trip
   constexpr int SLOT = BM * 20 + 20 * BN;  // floats per (stage, k-slot): A chunk then B chunk
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sbuf = reinterpret_cast<float*>(smem_raw);              // [NST][KS][SLOT]
@@ -375,7 +372,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int hw_out = a.Hout * a.Wout;
-  for (int r = tid; r < BM; r += CONV_THREADS) {
+  for (int r = tid; r < BM; r += THREADS) {
     const int m = m0 + r;
     if (m < a.M) {
       const int n = m / hw_out, rem = m - n * hw_out;
@@ -394,46 +391,48 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a
   const int nchunks = a.ks * a.ks * cpk;
   const int niter = (nchunks + KS - 1) / KS;
 
-  // all threads stage the (up to) four chunks of iteration `it` into stage `buf`
+  // all threads stage the (up to) KS chunks of iteration `it` into stage `buf`: one (chunk, pixel row) pair
+  // per thread and trip, so the staging is as wide as the CTA
   auto load_iter = [&](int it, int buf) {
-    for (int slot = 0; slot < KS; ++slot) {
+    for (int idx = tid; idx < KS * BM; idx += THREADS) {
+      const int slot = idx / BM, r = idx - slot * BM;
       const int c = it * KS + slot;
-      if (c >= nchunks) break;
+      if (c >= nchunks) continue;
       const int tap = c / cpk, ci0 = (c - tap * cpk) * 20;
       const int kh = tap / a.ks, kw = tap - kh * a.ks;
-      float* dA = sbuf + (buf * KS + slot) * SLOT;
-      for (int r = tid; r < BM; r += CONV_THREADS) {
-        int hi, wi;
-        bool ok;
-        if (!a.transposed) {
-          hi = s_h0[r] + kh;
-          wi = s_w0[r] + kw;
-          ok = (unsigned)hi < (unsigned)a.Hin && (unsigned)wi < (unsigned)a.Win;
+      int hi, wi;
+      bool ok;
+      if (!a.transposed) {
+        hi = s_h0[r] + kh;
+        wi = s_w0[r] + kw;
+        ok = (unsigned)hi < (unsigned)a.Hin && (unsigned)wi < (unsigned)a.Win;
+      } else {
+        const int th = s_h0[r] - kh, tw = s_w0[r] - kw;
+        ok = (th >= 0) && (tw >= 0);
+        if (a.stride == 2) {
+          ok = ok && (((th | tw) & 1) == 0);
+          hi = th >> 1;
+          wi = tw >> 1;
         } else {
-          const int th = s_h0[r] - kh, tw = s_w0[r] - kw;
-          ok = (th >= 0) && (tw >= 0);
-          if (a.stride == 2) {
-            ok = ok && (((th | tw) & 1) == 0);
-            hi = th >> 1;
-            wi = tw >> 1;
-          } else {
-            hi = th;
-            wi = tw;
-          }
-          ok = ok && hi < a.Hin && wi < a.Win;
+          hi = th;
+          wi = tw;
         }
-        const float* src = ok ? a.in + ((size_t)(s_base[r] + hi * a.Win + wi) * a.CK + ci0) : a.in;
-        const int nb = ok ? 16 : 0;
-        float* dst = dA + r * 20;
+        ok = ok && hi < a.Hin && wi < a.Win;
+      }
+      const float* src = ok ? a.in + ((size_t)(s_base[r] + hi * a.Win + wi) * a.CK + ci0) : a.in;
+      const int nb = ok ? 16 : 0;
+      float* dst = sbuf + (buf * KS + slot) * SLOT + r * 20;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) cp_async16(dst + q * 4, ok ? src + q * 4 : src, nb);
-      }
-      float* dB = dA + BM * 20;
+      for (int q = 0; q < 5; ++q) cp_async16(dst + q * 4, ok ? src + q * 4 : src, nb);
+    }
+    for (int idx = tid; idx < KS * 100; idx += THREADS) {
+      const int slot = idx / 100, rem = idx - slot * 100;
+      const int c = it * KS + slot;
+      if (c >= nchunks) continue;
+      const int tap = c / cpk, ci0 = (c - tap * cpk) * 20;
+      const int kk = rem / 5, q = rem - kk * 5;
       const float* wsrc = a.w + ((size_t)(a.flip ? a.ks * a.ks - 1 - tap : tap) * a.CK + ci0) * a.CN + n0;
-      for (int idx = tid; idx < 20 * (BN / 4); idx += CONV_THREADS) {
-        const int kk = idx / (BN / 4), q = idx - kk * (BN / 4);
-        cp_async16(dB + kk * BN + q * 4, wsrc + (size_t)kk * a.CN + q * 4, 16);
-      }
+      cp_async16(sbuf + (buf * KS + slot) * SLOT + BM * 20 + kk * BN + q * 4, wsrc + (size_t)kk * a.CN + q * 4, 16);
     }
   };
 
@@ -480,8 +479,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a
   }
   cp_async_wait<0>();
   __syncthreads();
-  // fixed-order combine of the four K-partials: warps 1..3 publish, warp 0 adds them in warp order
-  float* red = sbuf;  // [3][BM][20]  (all staging buffers are free now)
+  // fixed-order combine of the KS K-partials: warps 1.. publish, warp 0 adds them in warp order
+  float* red = sbuf;  // [KS-1][BM][20]  (all staging buffers are free now)
   if (warp > 0) {
 #pragma unroll
     for (int p = 0; p < PT; ++p)
@@ -493,7 +492,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a
   __syncthreads();
   if (warp == 0) {
 #pragma unroll
-    for (int w = 0; w < 3; ++w)
+    for (int w = 0; w < KS - 1; ++w)
 #pragma unroll
       for (int p = 0; p < PT; ++p)
 #pragma unroll
@@ -509,20 +508,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_ksplit_kernel(ConvArgs a
   conv_epilogue<20, PT, 1>(a, acc, mrow, n0, 0, 0, lane, tid, reinterpret_cast<double*>(smem_raw), warp == 0);
 }
 
-template <int PT>
+template <int PT, int KS>
 int launch_conv_ksplit(const ConvArgs& a, cudaStream_t stream) {
   constexpr int BM = 32 * PT;
-  constexpr int NST = (PT == 1) ? 4 : 3;
-  constexpr size_t smem = (size_t)(NST * 4 * (BM * 20 + 400)) * sizeof(float) + 3 * BM * sizeof(int);
+  constexpr int NST = (PT == 1 && KS == 4) ? 4 : 3;
+  constexpr size_t smem = (size_t)(NST * KS * (BM * 20 + 400)) * sizeof(float) + 3 * BM * sizeof(int);
   static bool configured = false;
   if (!configured) {
-    B200OCL_CUDA(cudaFuncSetAttribute(conv_ksplit_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200OCL_CUDA(cudaFuncSetAttribute(conv_ksplit_kernel<PT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   dim3 grid((a.M + BM - 1) / BM, a.CN / 20);
   B200OCL_PROF(a.transposed ? "conv_dgrad" : (a.mode == CONV_EVAL ? "conv_eval" : "conv_train"),
                2.0 * a.M * (double)a.CN * a.CK * a.ks * a.ks, stream);
-  conv_ksplit_kernel<PT><<<grid, CONV_THREADS, smem, stream>>>(a);
+  conv_ksplit_kernel<PT, KS><<<grid, 32 * KS, smem, stream>>>(a);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
 }
@@ -735,7 +734,11 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if (!best_bn) {
     if (a.ks * a.ks * (a.CK / 20) >= 4) {
       const long ctas2 = (long)((a.M + 63) / 64) * (a.CN / 20);
-      return ctas2 >= want ? launch_conv_ksplit<2>(a, stream) : launch_conv_ksplit<1>(a, stream);
+      if (ctas2 >= want) return launch_conv_ksplit<2, 4>(a, stream);
+      // fewer than two CTAs per SM and a long K: eight warps share the K loop
+      const long ctas1 = (long)((a.M + 31) / 32) * (a.CN / 20);
+      if (ctas1 < 2L * sm_count() && a.ks * a.ks * (a.CK / 20) >= 16) return launch_conv_ksplit<1, 8>(a, stream);
+      return launch_conv_ksplit<1, 4>(a, stream);
     }
     best_bn = 20;   // 1x1 convolutions with a short K: most CTAs
     best_pt = 1;

@@ -624,7 +624,12 @@ bool conv_tc_eligible(const ConvArgs& a) {
   if (a.Hin != a.Hout || a.Win != a.Wout) return false;
   // enough 128-pixel tiles to occupy a good part of the machine; small problems stay on the fp32 kernels
   const long ctas = (long)((a.M + 127) / 128) * (a.CN / a.tc_bn);
-  return ctas >= sm_count() / 4;
+  if (ctas < sm_count() / 4) return false;
+  // 20 -> 20 channels (layer 1): K = 180 leaves the tensor-core kernel dominated by its per-tile gather;
+  // measured (tools/net_layers.py) the fp32 patch kernel wins once there are >= ~2 tiles per SM
+  // (N = 110: 39 vs 57 us, N = 210: 66 vs 80 us) and loses below (N = 20: 35 vs 21 us).
+  if (a.CK == 20 && a.CN == 20 && ctas > 2L * sm_count()) return false;
+  return true;
 }
 
 int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {

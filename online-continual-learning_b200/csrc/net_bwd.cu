@@ -61,22 +61,30 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
     const float4 is = *reinterpret_cast<const float4*>(a.invstd + col * 4);
     const int r0 = blockIdx.x * a.rows_per_cta;
     const int r1 = min(a.M, r0 + a.rows_per_cta);
-    for (int r = r0 + rl; r < r1; r += R) {
-      const size_t i = (size_t)r * cols + col;
-      float4 g = reinterpret_cast<const float4*>(a.dA)[i];
-      if (a.amask) {
-        const float4 m = reinterpret_cast<const float4*>(a.amask)[i];
-        g.x = m.x > 0.f ? g.x : 0.f;
-        g.y = m.y > 0.f ? g.y : 0.f;
-        g.z = m.z > 0.f ? g.z : 0.f;
-        g.w = m.w > 0.f ? g.w : 0.f;
+    // four rows per trip: all twelve 16-byte loads are issued before the first use
+    for (int rb = r0 + rl; rb < r1; rb += 4 * R) {
+      float4 g[4], m[4], zz[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * R;
+        const size_t i = (size_t)(r < r1 ? r : rb) * cols + col;
+        g[u] = __ldg(reinterpret_cast<const float4*>(a.dA) + i);
+        zz[u] = __ldg(reinterpret_cast<const float4*>(a.z) + i);
+        m[u] = a.amask ? __ldg(reinterpret_cast<const float4*>(a.amask) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
       }
-      const float4 zz = reinterpret_cast<const float4*>(a.z)[i];
-      s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
-      q[0] = fmaf(g.x, (zz.x - mu.x) * is.x, q[0]);
-      q[1] = fmaf(g.y, (zz.y - mu.y) * is.y, q[1]);
-      q[2] = fmaf(g.z, (zz.z - mu.z) * is.z, q[2]);
-      q[3] = fmaf(g.w, (zz.w - mu.w) * is.w, q[3]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (rb + u * R >= r1) break;
+        const float gx = m[u].x > 0.f ? g[u].x : 0.f;
+        const float gy = m[u].y > 0.f ? g[u].y : 0.f;
+        const float gz = m[u].z > 0.f ? g[u].z : 0.f;
+        const float gw = m[u].w > 0.f ? g[u].w : 0.f;
+        s[0] += gx; s[1] += gy; s[2] += gz; s[3] += gw;
+        q[0] = fmaf(gx, (zz[u].x - mu.x) * is.x, q[0]);
+        q[1] = fmaf(gy, (zz[u].y - mu.y) * is.y, q[1]);
+        q[2] = fmaf(gz, (zz[u].z - mu.z) * is.z, q[2]);
+        q[3] = fmaf(gw, (zz[u].w - mu.w) * is.w, q[3]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -105,9 +113,19 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
   const int ch = tid % a.C, grp = tid / a.C;
   double S = 0.0, Q = 0.0;
   if (grp < groups) {
-    for (unsigned int b = grp; b < gridDim.x; b += groups) {
-      S += __ldcg(a.part + ((size_t)b * a.C + ch) * 2 + 0);
-      Q += __ldcg(a.part + ((size_t)b * a.C + ch) * 2 + 1);
+    unsigned int b = grp;
+    for (; b + 7u * groups < gridDim.x; b += 8u * groups) {   // eight loads in flight, fixed association
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = __ldcg(reinterpret_cast<const double2*>(a.part + ((size_t)(b + u * groups) * a.C + ch) * 2));
+      S += ((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x));
+      Q += ((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y));
+    }
+    for (; b < gridDim.x; b += groups) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(a.part + ((size_t)b * a.C + ch) * 2));
+      S += v.x;
+      Q += v.y;
     }
     sred[((size_t)grp * a.C + ch) * 2 + 0] = S;
     sred[((size_t)grp * a.C + ch) * 2 + 1] = Q;
@@ -213,6 +231,24 @@ __global__ void __launch_bounds__(128, 3) wgrad_kernel(WgradArgs a) {
   const int hw_out = a.Hout * a.Wout;
   const int nch = (m_end - m_begin + WG_MC - 1) / WG_MC;
 
+  // Per-thread gather constants: nthreads = 32*kw*nw is a multiple of the staged row length (kw*32
+  // k4-groups), so a thread always stages the same k4-group: its tap / channel offset is fixed and the
+  // per-pixel work is two compares and one add.
+  const int row_len = a.kw * 32;
+  const int gl = tid % row_len, pm0 = tid / row_len;   // pm = pm0 + it * nw
+  const int g4_mine = g4_base + gl;
+  bool k_ok = g4_mine < a.k4_groups;
+  int kh = 0, kwd = 0, k_off = 0;
+  if (k_ok) {
+    const int k = g4_mine * 4;
+    const int tap = k / a.Cin, ci = k - tap * a.Cin;
+    kh = tap / a.ks;
+    kwd = tap - kh * a.ks;
+    k_off = (kh * a.Win + kwd) * a.Cin + ci;
+  }
+  const int nq = NS / 4;                 // float4 per dz row: 5 or 10
+  const int dz_iters = (WG_MC * nq + nthreads - 1) / nthreads;
+
   auto rowinfo = [&](int c) {   // threads < MC
     if (tid < WG_MC) {
       int* inf = s_info + (c % (WG_NST + 1)) * 3 * WG_MC;
@@ -220,9 +256,10 @@ __global__ void __launch_bounds__(128, 3) wgrad_kernel(WgradArgs a) {
       if (c < nch && m < m_end) {
         const int n = m / hw_out, rem = m - n * hw_out;
         const int ho = rem / a.Wout, wo = rem - ho * a.Wout;
-        inf[tid] = n * a.Hin * a.Win;
-        inf[WG_MC + tid] = ho * a.stride - a.pad;
-        inf[2 * WG_MC + tid] = wo * a.stride - a.pad;
+        const int h0 = ho * a.stride - a.pad, w0 = wo * a.stride - a.pad;
+        inf[tid] = ((n * a.Hin + h0) * a.Win + w0) * a.Cin;   // element offset of the window origin (may be < 0)
+        inf[WG_MC + tid] = h0;
+        inf[2 * WG_MC + tid] = w0;
       } else {
         inf[tid] = 0;
         inf[WG_MC + tid] = -(1 << 20);
@@ -235,27 +272,22 @@ __global__ void __launch_bounds__(128, 3) wgrad_kernel(WgradArgs a) {
     float* sA = sbuf + (c % WG_NST) * stage_f;
     float* sG = sA + WG_MC * KS;
     const int m0 = m_begin + c * WG_MC;
-    for (int idx = tid; idx < WG_MC * a.kw * 32; idx += nthreads) {
-      const int pm = idx / (a.kw * 32), gl = idx - pm * (a.kw * 32);
-      const int g4 = g4_base + gl;
-      bool ok = g4 < a.k4_groups;
-      const float* src = a.x;
-      if (ok) {
-        const int k = g4 * 4;
-        const int tap = k / a.Cin, ci = k - tap * a.Cin;
-        const int kh = tap / a.ks, kwd = tap - kh * a.ks;
-        const int hi = inf[WG_MC + pm] + kh, wi = inf[2 * WG_MC + pm] + kwd;
-        ok = (unsigned)hi < (unsigned)a.Hin && (unsigned)wi < (unsigned)a.Win;
-        if (ok) src = a.x + ((size_t)(inf[pm] + hi * a.Win + wi) * a.Cin + ci);
-      }
+#pragma unroll 4
+    for (int pm = pm0; pm < WG_MC; pm += a.nw) {
+      const int hi = inf[WG_MC + pm] + kh, wi = inf[2 * WG_MC + pm] + kwd;
+      const bool ok = k_ok && (unsigned)hi < (unsigned)a.Hin && (unsigned)wi < (unsigned)a.Win;
+      const float* src = ok ? a.x + (inf[pm] + k_off) : a.x;
       cp_async16(sA + pm * KS + gl * 4, src, ok ? 16 : 0);
     }
-    for (int idx = tid; idx < WG_MC * (NS / 4); idx += nthreads) {
-      const int pm = idx / (NS / 4), q = idx - pm * (NS / 4);
-      const int m = m0 + pm;
-      const bool ok = (m < m_end) && (co_base + q * 4 < a.Cout);
-      const float* src = ok ? a.dz + (size_t)m * a.Cout + co_base + q * 4 : a.dz;
-      cp_async16(sG + pm * NS + q * 4, src, ok ? 16 : 0);
+    for (int it = 0; it < dz_iters; ++it) {
+      const int idx = tid + it * nthreads;
+      if (idx < WG_MC * nq) {
+        const int pm = idx / nq, q = idx - pm * nq;
+        const int m = m0 + pm;
+        const bool ok = (m < m_end) && (co_base + q * 4 < a.Cout);
+        const float* src = ok ? a.dz + (size_t)m * a.Cout + co_base + q * 4 : a.dz;
+        cp_async16(sG + pm * NS + q * 4, src, ok ? 16 : 0);
+      }
     }
   };
 
@@ -310,68 +342,148 @@ __global__ void __launch_bounds__(128, 3) wgrad_kernel(WgradArgs a) {
   }
 }
 
-// Stem weight gradient: dW[co][ci][kh][kw] over NCHW images; thread per (k, co), CTA per pixel range.
-__global__ void __launch_bounds__(576) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+// Stem weight gradient: dW[co][ci][kh][kw] over NCHW images.  A CTA owns a contiguous pixel range and
+// walks it in chunks of 128 pixels: the chunk's im2col values sx[27][128] and gradients sdz[128][20] are
+// staged in shared memory (coalesced), then 225 threads = 5 pixel slices x (9 taps x 5 channel quads)
+// accumulate 3 ci x 4 co each; the slices meet in shared memory in fixed order and the CTA writes one
+// partial [27][20].
+constexpr int SW_PX = 128, SW_LD = SW_PX + 4, SW_SLICES = 5;
+
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
                                                          float* __restrict__ part, int N, int H, int W, int M,
                                                          int pix_per_cta) {
+  __shared__ __align__(16) float sx[27 * SW_LD];
+  __shared__ __align__(16) float sdz[SW_PX * 20];
   const int tid = threadIdx.x;
-  const int k = tid / 20, co = tid - k * 20;  // k = tap*3 + ci
-  const bool active = tid < 540;
-  const int tap = k / 3, ci = k - tap * 3;
-  const int kh = tap / 3, kw = tap - kh * 3;
   const int hw = H * W;
   const int m0 = blockIdx.x * pix_per_cta, m1 = min(M, m0 + pix_per_cta);
-  float acc = 0.f;
-  if (active) {
-    float a4[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int mb = m0; mb < m1; mb += 4) {
-      float xv[4], gv[4];
+  const int slice = tid / 45, j = tid - slice * 45;
+  const int tap = j / 5, cq = j - tap * 5;
+  const bool worker = slice < SW_SLICES;
+  const int pl = tid & (SW_PX - 1), k0 = tid >> 7;   // staging role: pixel pl, k = k0, k0 + 2, ...
+  float acc[3][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {      // four independent load pairs in flight
-        const int m = mb + u;
-        xv[u] = 0.f;
-        gv[u] = 0.f;
-        if (m < m1) {
-          const int n = m / hw, rem = m - n * hw;
-          const int ho = rem / W, wo = rem - ho * W;
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+
+  for (int mc = m0; mc < m1; mc += SW_PX) {
+    __syncthreads();   // previous chunk fully consumed
+    {
+      const int m = mc + pl;
+      const bool pok = m < m1;
+      int n = 0, ho = 0, wo = 0;
+      if (pok) {
+        n = m / hw;
+        const int rem = m - n * hw;
+        ho = rem / W;
+        wo = rem - ho * W;
+      }
+      float v[14];
+#pragma unroll
+      for (int it = 0; it < 14; ++it) {
+        const int k = k0 + 2 * it;
+        v[it] = 0.f;
+        if (k < 27 && pok) {
+          const int tp = k / 3, ci = k - tp * 3;
+          const int kh = tp / 3, kw = tp - kh * 3;
           const int hi = ho + kh - 1, wi = wo + kw - 1;
-          if ((unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W) {
-            xv[u] = __ldg(x + ((size_t)(n * 3 + ci) * H + hi) * W + wi);
-            gv[u] = __ldg(dz + (size_t)m * 20 + co);
-          }
+          if ((unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W)
+            v[it] = __ldg(x + ((size_t)(n * 3 + ci) * H + hi) * W + wi);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a4[u] = fmaf(xv[u], gv[u], a4[u]);
+      for (int it = 0; it < 14; ++it) {
+        const int k = k0 + 2 * it;
+        if (k < 27) sx[k * SW_LD + pl] = v[it];
+      }
+      const int nvec = SW_PX * 5;
+      for (int idx = tid; idx < nvec; idx += 256) {
+        const int pm = idx / 5;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mc + pm < m1) g = __ldg(reinterpret_cast<const float4*>(dz + (size_t)mc * 20) + idx);
+        reinterpret_cast<float4*>(sdz)[idx] = g;
+      }
     }
-    acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
-    part[(size_t)blockIdx.x * 540 + k * 20 + co] = acc;
+    __syncthreads();
+    if (worker) {
+      const float* px = sx + tap * 3 * SW_LD;
+#pragma unroll 2
+      for (int p = slice; p < SW_PX; p += SW_SLICES) {
+        const float4 g = *reinterpret_cast<const float4*>(sdz + p * 20 + cq * 4);
+        const float x0 = px[p], x1 = px[SW_LD + p], x2 = px[2 * SW_LD + p];
+        acc[0][0] = fmaf(x0, g.x, acc[0][0]); acc[0][1] = fmaf(x0, g.y, acc[0][1]);
+        acc[0][2] = fmaf(x0, g.z, acc[0][2]); acc[0][3] = fmaf(x0, g.w, acc[0][3]);
+        acc[1][0] = fmaf(x1, g.x, acc[1][0]); acc[1][1] = fmaf(x1, g.y, acc[1][1]);
+        acc[1][2] = fmaf(x1, g.z, acc[1][2]); acc[1][3] = fmaf(x1, g.w, acc[1][3]);
+        acc[2][0] = fmaf(x2, g.x, acc[2][0]); acc[2][1] = fmaf(x2, g.y, acc[2][1]);
+        acc[2][2] = fmaf(x2, g.z, acc[2][2]); acc[2][3] = fmaf(x2, g.w, acc[2][3]);
+      }
+    }
+  }
+  __syncthreads();
+  float* red = sx;   // [SLICES][540] = 2700 floats <= 27 * 132
+  if (worker) {
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) red[slice * 540 + (tap * 3 + ci) * 20 + cq * 4 + c] = acc[ci][c];
+  }
+  __syncthreads();
+  for (int e = tid; e < 540; e += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < SW_SLICES; ++sl) s += red[sl * 540 + e];
+    part[(size_t)blockIdx.x * 540 + e] = s;
   }
 }
 
-// One launch reduces the partials of every conv layer and writes OIHW gradients.
+// One launch reduces the partials of every conv layer and writes OIHW gradients.  A CTA owns EPB = 256 / SG
+// consecutive gradient elements of one layer; its SG thread groups each sum every SG-th split (eight loads in
+// flight, fixed association), the groups meet in shared memory in fixed order.  SG grows with the layer's
+// split count so that no thread walks more than a few dozen partials.
 struct WgFinalTable {
   int n;
+  unsigned int n_blocks;
   struct {
     unsigned long long part_off;
-    unsigned int w_off;
-    int splits, cin, cout, taps;
+    unsigned int w_off, blk_start;
+    int splits, cin, cout, taps, sg_log2;
   } e[NET_MAX_CONV];
 };
 
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(WgFinalTable t, const float* __restrict__ part,
                                                              float* __restrict__ grads, int accumulate) {
-  const auto& L = t.e[blockIdx.y];
+  __shared__ float red[256];
+  int l = 0;
+  while (l + 1 < t.n && blockIdx.x >= t.e[l + 1].blk_start) ++l;
+  const auto& L = t.e[l];
+  const int SG = 1 << L.sg_log2, EPB = 256 >> L.sg_log2;
+  const int el = threadIdx.x & (EPB - 1), sg = threadIdx.x >> (8 - L.sg_log2);
   const int K = L.cin * L.taps;
   const int total = K * L.cout;
-  const float* p = part + L.part_off;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+  const int e = (int)(blockIdx.x - L.blk_start) * EPB + el;
+  float s = 0.f;
+  if (e < total) {
+    const float* p = part + L.part_off + e;
+    int sp = sg;
+    for (; sp + 7 * SG < L.splits; sp += 8 * SG) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(p + (size_t)(sp + u * SG) * total);
+      s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    for (; sp < L.splits; sp += SG) s += __ldcs(p + (size_t)sp * total);
+  }
+  red[threadIdx.x] = s;   // [sg][el]
+  __syncthreads();
+  if (sg == 0 && e < total) {
+    float tot = 0.f;
+    for (int g = 0; g < SG; ++g) tot += red[g * EPB + el];
     const int k = e / L.cout, co = e - k * L.cout;
-    float s = 0.f;
-    for (int sp = 0; sp < L.splits; ++sp) s += p[(size_t)sp * total + e];
     const int tap = k / L.cin, ci = k - tap * L.cin;
     float* dst = grads + L.w_off + ((size_t)co * L.cin + ci) * L.taps + tap;
-    if (accumulate) *dst += s; else *dst = s;
+    if (accumulate) *dst += tot; else *dst = tot;
   }
 }
 
@@ -620,24 +732,32 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
   if ((rc = bn_backward(0, g0, w.a + (size_t)N * p.conv[0].act_off, w.g2, nullptr))) return rc;
   {
     const int M = N * p.in_h * p.in_w;
-    const int ctas = 8 * sms;
-    const int ppc = (M + ctas - 1) / ctas;
+    int ctas = (M + SW_PX - 1) / SW_PX;
+    if (ctas > 2 * sms) ctas = 2 * sms;
+    const int ppc = ((M + ctas - 1) / ctas + SW_PX - 1) / SW_PX * SW_PX;
     const int grid = (M + ppc - 1) / ppc;
     B200OCL_PROF("wgrad", 2.0 * M * 540.0, stream);
-    stem_wgrad_kernel<<<grid, 576, 0, stream>>>(x, w.g2, w.wg_part + w.wg_off[0], N, p.in_h, p.in_w, M, ppc);
+    stem_wgrad_kernel<<<grid, 256, 0, stream>>>(x, w.g2, w.wg_part + w.wg_off[0], N, p.in_h, p.in_w, M, ppc);
     B200OCL_LAUNCHED();
     WgFinalTable t{};
     t.n = p.n_conv;
+    unsigned int blocks = 0;
     for (int i = 0; i < p.n_conv; ++i) {
-      t.e[i].part_off = w.wg_off[i];
-      t.e[i].w_off = (unsigned)p.conv[i].w_off;
-      t.e[i].cin = p.conv[i].cin;
-      t.e[i].cout = p.conv[i].cout;
-      t.e[i].taps = p.conv[i].ks * p.conv[i].ks;
-      t.e[i].splits = (i == 0) ? grid : wgrad_cfg(p.conv[i], N, sms).splits;
+      auto& e = t.e[i];
+      e.part_off = w.wg_off[i];
+      e.w_off = (unsigned)p.conv[i].w_off;
+      e.cin = p.conv[i].cin;
+      e.cout = p.conv[i].cout;
+      e.taps = p.conv[i].ks * p.conv[i].ks;
+      e.splits = (i == 0) ? grid : wgrad_cfg(p.conv[i], N, sms).splits;
+      e.sg_log2 = e.splits >= 256 ? 5 : (e.splits >= 64 ? 4 : (e.splits >= 16 ? 3 : 2));
+      e.blk_start = blocks;
+      const int epb = 256 >> e.sg_log2;
+      blocks += (unsigned)((e.cin * e.taps * e.cout + epb - 1) / epb);
     }
+    t.n_blocks = blocks;
     B200OCL_PROF("wgrad_finalize", 8.0 * p.n_packed / 2, stream);
-    wgrad_finalize_kernel<<<dim3(128, p.n_conv), 256, 0, stream>>>(t, w.wg_part, st->grads, accumulate);
+    wgrad_finalize_kernel<<<blocks, 256, 0, stream>>>(t, w.wg_part, st->grads, accumulate);
     B200OCL_LAUNCHED();
   }
   return B200OCL_OK;

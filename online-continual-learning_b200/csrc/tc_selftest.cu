@@ -101,6 +101,72 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
   if (warp == 0) umma::tmem_dealloc(tmem, ncols);
 }
 
+// Window test: the A operand is NOT a packed tile but a window into a larger swizzled buffer of 128-byte
+// rows ("patch"): tile row 8g + r is patch row start_row + g * sbo_rows + r.  The patch is stored with the
+// swizzle keyed on the absolute row index (row & 7), the start address is not 1024-byte aligned when
+// start_row % 8 != 0, and the descriptor's base-offset field (bits 49..51) is set to start_row & 7 when
+// base_off_mode == 1.  This is what lets a convolution feed the tensor core straight from a halo patch.
+__global__ void __launch_bounds__(128) umma_window_kernel(const float* __restrict__ P, const float* __restrict__ B,
+                                                          float* __restrict__ D, int rows, int start_row, int sbo_rows,
+                                                          int base_off_mode, int N, int* __restrict__ status) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* sP = reinterpret_cast<float*>(smem_raw);           // rows x 32 fp32
+  float* sB = sP + (size_t)((rows + 7) / 8 * 8) * 32;       // 1024-byte aligned
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_slot, ncols);
+  if (tid == 0) {
+    umma::mbar_init(&mbar, 1);
+    umma::fence_mbar_init();
+  }
+  for (int idx = tid; idx < rows * 8; idx += 128) {
+    const int r = idx >> 3, c = idx & 7;
+    *reinterpret_cast<float4*>(sP + umma::sw128_offset_f32(r, c)) = *reinterpret_cast<const float4*>(P + (size_t)r * 32 + c * 4);
+  }
+  for (int idx = tid; idx < N * 8; idx += 128) {
+    const int r = idx >> 3, c = idx & 7;
+    *reinterpret_cast<float4*>(sB + umma::sw128_offset_f32(r, c)) = *reinterpret_cast<const float4*>(B + (size_t)r * 32 + c * 4);
+  }
+  umma::fence_proxy_async_smem();
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t idesc = umma::make_idesc_tf32(128, N);
+  if (tid == 0) {
+    uint64_t dA = umma::make_smem_desc_sw128(umma::smem_u32(sP) + (uint32_t)start_row * 128u);
+    dA &= ~((uint64_t)0x3FFF << 32);
+    dA |= (uint64_t)(((uint32_t)sbo_rows * 128u >> 4) & 0x3FFF) << 32;
+    if (base_off_mode == 1) dA |= (uint64_t)(start_row & 7) << 49;
+    const uint64_t dB = umma::make_smem_desc_sw128(umma::smem_u32(sB));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t adv = (uint64_t)(k * 32 >> 4);
+      umma::mma_tf32_ss(tmem, dA + adv, dB + adv, idesc, k > 0 ? 1u : 0u);
+    }
+    umma::mma_commit(&mbar);
+  }
+  const bool ok = umma::mbar_wait(&mbar, 0);
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  if (ok) {
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16];
+      umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) D[(size_t)row * N + c0 + j] = v[j];
+    }
+  }
+  if (tid == 0) *status = ok ? 0 : 1;
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
 }  // namespace
 }  // namespace b200ocl
 
@@ -117,6 +183,22 @@ extern "C" int b200ocl_selftest_umma_tf32(const float* A, const float* B, float*
     configured = true;
   }
   umma_selftest_kernel<<<1, 128, smem, stream>>>(A, B, D, N, K, mode, status);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
+
+extern "C" int b200ocl_selftest_umma_window(const float* P, const float* B, float* D, int rows, int start_row,
+                                            int sbo_rows, int base_off_mode, int N, int* status, void* stream_) {
+  using namespace b200ocl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200OCL_CHECK_ARG(P && B && D && status, "null pointer");
+  B200OCL_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0, "need N in [16,256] %16");
+  B200OCL_CHECK_ARG(rows > 0 && rows <= 1024 && start_row >= 0 && sbo_rows > 0 &&
+                        start_row + 15 * sbo_rows + 8 <= rows,
+                    "window exceeds the patch");
+  const size_t smem = (size_t)((rows + 7) / 8 * 8 + 256) * 32 * sizeof(float) + 1024;
+  B200OCL_CUDA(cudaFuncSetAttribute(umma_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_window_kernel<<<1, 128, smem, stream>>>(P, B, D, rows, start_row, sbo_rows, base_off_mode, N, status);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
 }
