@@ -90,6 +90,15 @@ int b200ocl_supcon(const float* feats, const int64_t* labels, int B, int V, int 
 int b200ocl_gather_rows(const void* src, const int64_t* idx, int n_rows, size_t row_bytes, void* dst, void* stream);
 int b200ocl_scatter_rows(const void* src, const int64_t* idx, int n_rows, size_t row_bytes, void* dst, void* stream);
 
+/* ASER memory replacement on the device (reference utils/buffer/aser_update.py:88-112: current samples ranked
+ * inside the first n_cand_buf places of the descending SV ranking replace, pairwise in rank order, the buffered
+ * candidates ranked below).  order[n_total] ranks positions of [buffered candidates | current batch];
+ * cand_slot[n_cand_buf] are the candidates' buffer slots.  Moves image rows and labels; pairs_out (nullable,
+ * [1 + 2*n_cur] int64 = count, src positions, dst slots, -1 padded) lets the host mirror follow asynchronously. */
+int b200ocl_aser_replace(const int64_t* order, int n_total, int n_cand_buf, const int64_t* cand_slot, const void* cur_x,
+                         const int64_t* cur_y, int n_cur, size_t row_bytes, void* buffer_img, int64_t* buffer_label,
+                         int64_t* pairs_out, void* stream);
+
 /* ---------------------------------------------------------------- SGD
  * p -= lr * (g + wd * p) over a flat arena of n floats: torch.optim.SGD without
  * momentum (utils/setup_elements.py:73-75) and MIR's virtual step

@@ -36,6 +36,7 @@ SIGNATURES = {
     'b200ocl_net_sgd_step': (c_int, [P, P, c_float, c_float, P, P]),
     'b200ocl_ce_loss': (c_int, [P, P, c_int, c_int, P, P, P, P, P]),
     'b200ocl_scr_augment': (c_int, [P, P, P, c_int, c_int, c_int, P]),
+    'b200ocl_aser_replace': (c_int, [P, c_int, c_int, P, P, P, c_int, c_size_t, P, P, P, P]),
     'b200ocl_selftest_umma_tf32': (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
     'b200ocl_selftest_umma_window': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
 }

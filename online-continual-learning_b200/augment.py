@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _native
+from .memory import to_device
 from .ops import _need_cuda, _stream
 
 
@@ -25,16 +26,16 @@ def draw_params(n, height, width, rng=None, scale=(0.2, 1.0), ratio=(3. / 4., 4.
     rng = np.random if rng is None else rng
     out = np.zeros((n, 12), dtype=np.float32)
     # RandomResizedCrop: area ~ U(scale)*H*W, log-uniform aspect; 10 tries, else the whole image
-    w = np.full(n, float(width))
-    h = np.full(n, float(height))
-    done = np.zeros(n, dtype=bool)
-    for _ in range(10):
-        area = rng.uniform(scale[0], scale[1], n) * height * width
-        aspect = np.exp(rng.uniform(math.log(ratio[0]), math.log(ratio[1]), n))
-        tw, th = np.floor(np.sqrt(area * aspect)), np.floor(np.sqrt(area / aspect))
-        ok = (~done) & (tw >= 1) & (tw <= width) & (th >= 1) & (th <= height)
-        w[ok], h[ok] = tw[ok], th[ok]
-        done |= ok
+    tries = 10
+    area = rng.uniform(scale[0], scale[1], (tries, n)) * height * width
+    aspect = np.exp(rng.uniform(math.log(ratio[0]), math.log(ratio[1]), (tries, n)))
+    tw, th = np.floor(np.sqrt(area * aspect)), np.floor(np.sqrt(area / aspect))
+    ok = (tw >= 1) & (tw <= width) & (th >= 1) & (th <= height)
+    first = ok.argmax(axis=0)                      # first successful try per sample
+    any_ok = ok.any(axis=0)
+    cols = np.arange(n)
+    w = np.where(any_ok, tw[first, cols], float(width))
+    h = np.where(any_ok, th[first, cols], float(height))
     out[:, 2], out[:, 3] = w, h
     out[:, 0] = np.floor(rng.uniform(0, 1, n) * (width - w + 1))
     out[:, 1] = np.floor(rng.uniform(0, 1, n) * (height - h + 1))
@@ -67,7 +68,7 @@ class SCRTransform(torch.nn.Module):
             raise ValueError('expected [N,3,%d,%d] images' % self.size)
         if params is None:
             params = draw_params(n, h, w, scale=self.scale)
-        p = torch.from_numpy(np.ascontiguousarray(params, dtype=np.float32)).to(x.device)
+        p = to_device(np.ascontiguousarray(params, dtype=np.float32), x.device)
         out = torch.empty_like(x)
         rc = _native.lib().b200ocl_scr_augment(x.data_ptr(), out.data_ptr(), p.data_ptr(), n, h, w, _stream())
         _native.check(rc, 'b200ocl_scr_augment')

@@ -41,6 +41,48 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// Pixel enumeration.  Default: m = (n, ho, wo) row-major.  With parity_order (stride-2 data gradient, even
+// Hout / Wout): m = (class, n, ho/2, wo/2), class = 2*(ho&1) + (wo&1) -- a tile then holds pixels of one parity
+// class, for which only the taps with kh = ho + pad (mod 2), kw = wo + pad (mod 2) contribute.
+__device__ __forceinline__ void decode_pixel(const ConvArgs& a, int m, int& n, int& ho, int& wo) {
+  if (a.parity_order) {
+    const int hh = a.Hout >> 1, wh = a.Wout >> 1;
+    const int mq = a.N * hh * wh;
+    const int cls = m / mq;
+    int idx = m - cls * mq;
+    n = idx / (hh * wh);
+    idx -= n * hh * wh;
+    const int y = idx / wh;
+    ho = 2 * y + (cls >> 1);
+    wo = 2 * (idx - y * wh) + (cls & 1);
+  } else {
+    const int hw_out = a.Hout * a.Wout;
+    n = m / hw_out;
+    const int rem = m - n * hw_out;
+    ho = rem / a.Wout;
+    wo = rem - ho * a.Wout;
+  }
+}
+// Taps a tile of pixels [m0, m0 + bm) can use, as a packed list: nibble i = i-th usable tap, count in `n`.
+__device__ __forceinline__ unsigned long long tile_tap_list(const ConvArgs& a, int m0, int bm, int& n) {
+  unsigned long long list = 0;
+  n = 0;
+  if (!a.parity_order) {
+    n = a.ks * a.ks;
+    return 0x876543210ull;
+  }
+  const int mq = a.N * (a.Hout >> 1) * (a.Wout >> 1);
+  const int c0 = m0 / mq, c1 = min(m0 + bm - 1, a.M - 1) / mq;
+  for (int kh = 0; kh < a.ks; ++kh)
+    for (int kw = 0; kw < a.ks; ++kw) {
+      bool live = false;
+      for (int cls = c0; cls <= c1; ++cls)
+        live = live || ((((cls >> 1) + a.pad - kh) & 1) == 0 && (((cls & 1) + a.pad - kw) & 1) == 0);
+      if (live) list |= (unsigned long long)(kh * a.ks + kw) << (4 * n++);
+    }
+  return list;
+}
+
 // Shared epilogue: thread holds acc[PT][20] for rows r = row_base + 32*p (p < PT) and
 // channels n0 + wn*20 .. +19.  `scratch` is >= 4*20*2 doubles of shared memory, free to use.
 template <int BN, int PT, int WM = 4 / (BN / 20)>
@@ -196,33 +238,38 @@ __global__ void __launch_bounds__(CONV_THREADS, (PT <= 2 ? 4 : 3)) conv_kernel(C
   int* s_base = reinterpret_cast<int*>(sB + NST * 20 * BN);
   int* s_h0 = s_base + BM;
   int* s_w0 = s_h0 + BM;
+  int* s_m = s_w0 + BM;   // real (row-major) pixel index of each tile row, -1 past the end
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / WN, wn = warp % WN;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int hw_out = a.Hout * a.Wout;
 
   for (int r = tid; r < BM; r += CONV_THREADS) {
     const int m = m0 + r;
     if (m < a.M) {
-      const int n = m / hw_out, rem = m - n * hw_out;
-      const int ho = rem / a.Wout, wo = rem - ho * a.Wout;
+      int n, ho, wo;
+      decode_pixel(a, m, n, ho, wo);
       s_base[r] = n * a.Hin * a.Win;
       s_h0[r] = a.transposed ? ho + a.pad : ho * a.stride - a.pad;
       s_w0[r] = a.transposed ? wo + a.pad : wo * a.stride - a.pad;
+      s_m[r] = (n * a.Hout + ho) * a.Wout + wo;
     } else {
       s_base[r] = 0;
       s_h0[r] = -(1 << 20);
       s_w0[r] = -(1 << 20);
+      s_m[r] = -1;
     }
   }
   __syncthreads();
 
   const int cpk = a.CK / 20;
-  const int nchunks = a.ks * a.ks * cpk;
+  int ntaps;
+  const unsigned long long tap_list = tile_tap_list(a, m0, BM, ntaps);
+  const int nchunks = ntaps * cpk;
 
   auto load_chunk = [&](int c, int buf) {
-    const int tap = c / cpk, ci0 = (c - tap * cpk) * 20;
+    const int ti = c / cpk, ci0 = (c - ti * cpk) * 20;
+    const int tap = (int)((tap_list >> (4 * ti)) & 15ull);
     const int kh = tap / a.ks, kw = tap - kh * a.ks;
     float* dA = sA + buf * BM * 20;
     for (int r = tid; r < BM; r += CONV_THREADS) {   // one thread stages a whole 80-byte row
@@ -303,7 +350,8 @@ __global__ void __launch_bounds__(CONV_THREADS, (PT <= 2 ? 4 : 3)) conv_kernel(C
   __syncthreads();
   int mrow[PT];
 #pragma unroll
-  for (int p = 0; p < PT; ++p) mrow[p] = (m0 + row_base + 32 * p < a.M) ? m0 + row_base + 32 * p : -1;
+  for (int p = 0; p < PT; ++p) mrow[p] = s_m[row_base + 32 * p];
+  __syncthreads();   // s_m read before the epilogue reuses the front of shared memory
   conv_epilogue<BN, PT>(a, acc, mrow, n0, wm, wn, lane, tid, reinterpret_cast<double*>(smem_raw));
 }
 
@@ -368,27 +416,31 @@ __global__ void __launch_bounds__(32 * KS, (KS == 4 ? 4 : 1)) conv_ksplit_kernel
   int* s_base = reinterpret_cast<int*>(sbuf + NST * KS * SLOT);  // [BM]
   int* s_h0 = s_base + BM;
   int* s_w0 = s_h0 + BM;
+  int* s_m = s_w0 + BM;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int hw_out = a.Hout * a.Wout;
   for (int r = tid; r < BM; r += THREADS) {
     const int m = m0 + r;
     if (m < a.M) {
-      const int n = m / hw_out, rem = m - n * hw_out;
-      const int ho = rem / a.Wout, wo = rem - ho * a.Wout;
+      int n, ho, wo;
+      decode_pixel(a, m, n, ho, wo);
       s_base[r] = n * a.Hin * a.Win;
       s_h0[r] = a.transposed ? ho + a.pad : ho * a.stride - a.pad;
       s_w0[r] = a.transposed ? wo + a.pad : wo * a.stride - a.pad;
+      s_m[r] = (n * a.Hout + ho) * a.Wout + wo;
     } else {
       s_base[r] = 0;
       s_h0[r] = -(1 << 20);
       s_w0[r] = -(1 << 20);
+      s_m[r] = -1;
     }
   }
   __syncthreads();
   const int cpk = a.CK / 20;
-  const int nchunks = a.ks * a.ks * cpk;
+  int ntaps;
+  const unsigned long long tap_list = tile_tap_list(a, m0, BM, ntaps);
+  const int nchunks = ntaps * cpk;
   const int niter = (nchunks + KS - 1) / KS;
 
   // all threads stage the (up to) KS chunks of iteration `it` into stage `buf`: one (chunk, pixel row) pair
@@ -398,7 +450,8 @@ __global__ void __launch_bounds__(32 * KS, (KS == 4 ? 4 : 1)) conv_ksplit_kernel
       const int slot = idx / BM, r = idx - slot * BM;
       const int c = it * KS + slot;
       if (c >= nchunks) continue;
-      const int tap = c / cpk, ci0 = (c - tap * cpk) * 20;
+      const int ti = c / cpk, ci0 = (c - ti * cpk) * 20;
+      const int tap = (int)((tap_list >> (4 * ti)) & 15ull);
       const int kh = tap / a.ks, kw = tap - kh * a.ks;
       int hi, wi;
       bool ok;
@@ -429,7 +482,8 @@ __global__ void __launch_bounds__(32 * KS, (KS == 4 ? 4 : 1)) conv_ksplit_kernel
       const int slot = idx / 100, rem = idx - slot * 100;
       const int c = it * KS + slot;
       if (c >= nchunks) continue;
-      const int tap = c / cpk, ci0 = (c - tap * cpk) * 20;
+      const int ti = c / cpk, ci0 = (c - ti * cpk) * 20;
+      const int tap = (int)((tap_list >> (4 * ti)) & 15ull);
       const int kk = rem / 5, q = rem - kk * 5;
       const float* wsrc = a.w + ((size_t)(a.flip ? a.ks * a.ks - 1 - tap : tap) * a.CK + ci0) * a.CN + n0;
       cp_async16(sbuf + (buf * KS + slot) * SLOT + BM * 20 + kk * BN + q * 4, wsrc + (size_t)kk * a.CN + q * 4, 16);
@@ -504,7 +558,8 @@ __global__ void __launch_bounds__(32 * KS, (KS == 4 ? 4 : 1)) conv_ksplit_kernel
   __syncthreads();
   int mrow[PT];
 #pragma unroll
-  for (int p = 0; p < PT; ++p) mrow[p] = (m0 + lane + 32 * p < a.M) ? m0 + lane + 32 * p : -1;
+  for (int p = 0; p < PT; ++p) mrow[p] = s_m[lane + 32 * p];
+  __syncthreads();
   conv_epilogue<20, PT, 1>(a, acc, mrow, n0, 0, 0, lane, tid, reinterpret_cast<double*>(smem_raw), warp == 0);
 }
 
@@ -512,7 +567,7 @@ template <int PT, int KS>
 int launch_conv_ksplit(const ConvArgs& a, cudaStream_t stream) {
   constexpr int BM = 32 * PT;
   constexpr int NST = (PT == 1 && KS == 4) ? 4 : 3;
-  constexpr size_t smem = (size_t)(NST * KS * (BM * 20 + 400)) * sizeof(float) + 3 * BM * sizeof(int);
+  constexpr size_t smem = (size_t)(NST * KS * (BM * 20 + 400)) * sizeof(float) + 4 * BM * sizeof(int);
   static bool configured = false;
   if (!configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(conv_ksplit_kernel<PT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -671,7 +726,7 @@ int launch_conv_patch(ConvArgs a, const PatchTile& t, cudaStream_t stream) {
 template <int BN, int PT>
 int launch_conv_cfg(const ConvArgs& a, cudaStream_t stream) {
   constexpr int WN = BN / 20, WM = 4 / WN, BM = WM * 32 * PT;
-  constexpr size_t smem = (size_t)(3 * BM * 20 + 3 * 20 * BN) * sizeof(float) + 3 * BM * sizeof(int);
+  constexpr size_t smem = (size_t)(3 * BM * 20 + 3 * 20 * BN) * sizeof(float) + 4 * BM * sizeof(int);
   static bool configured = false;
   if (!configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(conv_kernel<BN, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -22,6 +22,8 @@ struct ConvArgs {
                      //    (input pixel (t/stride) with t = ho + pad - kh, only when divisible)
   const float* w_tc; // tensor-core operand image of the same weights (net_plan.cuh), nullable
   int tc_kb, tc_bn;  // its K blocks and real channels per tile
+  int parity_order;  // stride-2 data gradient only: pixels enumerated [parity class][n][h/2][w/2] so that a CTA
+                     //    sees one class and skips the taps that cannot reach it (9 of 36 tap-pixel pairs are live)
   int flip;          // patch kernel only: use tap (ks*ks-1-tap) of the weights (stride-1 data gradient)
   int th, tw, ti;    // patch kernel only: spatial tile (rows, cols, images), set by the launcher
   int M;             // N*Hout*Wout output pixels

@@ -84,6 +84,71 @@ int move_rows(const void* src, const int64_t* idx, int n_rows, size_t row_bytes,
   return B200OCL_OK;
 }
 
+// ----------------------------------------------------------------------------- ASER memory replacement
+// Replacement rule of reference utils/buffer/aser_update.py:88-112 taken on the device.  `order` is the
+// descending SV ranking over [buffered candidates (n_cand_buf) | current batch (n_cur)].  Current samples
+// ranked inside the first n_cand_buf places replace, pairwise in rank order, the buffered candidates
+// ranked below them:  buffer[cand_slot[small_j]] <- cur[large_j - n_cand_buf].  CTA j finds the j-th pair
+// by a ballot scan of the ranking (one warp, <= 4096 ranks) and moves that row; CTA 0 also publishes
+// pairs_out = [count, src_0.., dst_0..] (src/dst padded with -1) for the host mirror, read asynchronously.
+__global__ void __launch_bounds__(256) aser_replace_kernel(const long long* __restrict__ order, int n_total,
+                                                           int n_cand_buf, const long long* __restrict__ cand_slot,
+                                                           const unsigned char* __restrict__ cur_x,
+                                                           const long long* __restrict__ cur_y, int n_cur,
+                                                           size_t row_bytes, unsigned char* __restrict__ buffer_img,
+                                                           long long* __restrict__ buffer_label,
+                                                           long long* __restrict__ pairs_out) {
+  __shared__ long long s_src, s_dst;
+  __shared__ int s_count;
+  const int j = blockIdx.x;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    long long src = -1, dst = -1;
+    int seen_cur = 0, seen_buf = 0;
+    // top part: the j-th current-batch sample in rank order
+    for (int base = 0; base < n_cand_buf; base += 32) {
+      const int r = base + lane;
+      const long long o = (r < n_cand_buf) ? order[r] : -1;
+      const bool f = o >= n_cand_buf;
+      const unsigned int m = __ballot_sync(0xffffffffu, f);
+      const int before = seen_cur + __popc(m & ((1u << lane) - 1u));
+      if (f && before == j) src = o - n_cand_buf;
+      seen_cur += __popc(m);
+    }
+    // bottom part: the j-th buffered candidate in rank order
+    for (int base = n_cand_buf; base < n_total; base += 32) {
+      const int r = base + lane;
+      const long long o = (r < n_total) ? order[r] : (long long)n_cand_buf;
+      const bool f = o < n_cand_buf;
+      const unsigned int m = __ballot_sync(0xffffffffu, f);
+      const int before = seen_buf + __popc(m & ((1u << lane) - 1u));
+      if (f && before == j) dst = cand_slot[o];
+      seen_buf += __popc(m);
+    }
+    // exactly one lane (or none) holds each value
+    for (int o = 16; o > 0; o >>= 1) {
+      src = max(src, __shfl_xor_sync(0xffffffffu, src, o));
+      dst = max(dst, __shfl_xor_sync(0xffffffffu, dst, o));
+    }
+    if (lane == 0) {
+      s_src = src;
+      s_dst = dst;
+      s_count = seen_cur;   // == seen_buf by counting
+      if (pairs_out) {
+        if (j == 0) pairs_out[0] = seen_cur;
+        pairs_out[1 + j] = (j < seen_cur) ? src : -1;
+        pairs_out[1 + n_cur + j] = (j < seen_cur) ? dst : -1;
+      }
+    }
+  }
+  __syncthreads();
+  if (j >= s_count || s_src < 0 || s_dst < 0) return;
+  const uint4* s = reinterpret_cast<const uint4*>(cur_x + (size_t)s_src * row_bytes);
+  uint4* d = reinterpret_cast<uint4*>(buffer_img + (size_t)s_dst * row_bytes);
+  for (size_t v = threadIdx.x; v < row_bytes / 16; v += blockDim.x) d[v] = s[v];
+  if (threadIdx.x == 0) buffer_label[s_dst] = cur_y[s_src];
+}
+
 // ----------------------------------------------------------------------------- SGD
 __global__ void __launch_bounds__(256) sgd_kernel(const float* __restrict__ p, const float* __restrict__ g,
                                                   float* __restrict__ out, size_t n, float lr, float wd) {
@@ -134,6 +199,28 @@ int b200ocl_scatter_rows(const void* src, const int64_t* idx, int n_rows, size_t
   B200OCL_CHECK_ARG(n_rows >= 0 && row_bytes % 4 == 0, "need n_rows >= 0 and row_bytes % 4 == 0");
   B200OCL_CHECK_ARG(n_rows == 0 || (src && idx && dst), "null pointer");
   return move_rows<true>(src, idx, n_rows, row_bytes, dst, static_cast<cudaStream_t>(stream));
+}
+
+int b200ocl_aser_replace(const int64_t* order, int n_total, int n_cand_buf, const int64_t* cand_slot, const void* cur_x,
+                         const int64_t* cur_y, int n_cur, size_t row_bytes, void* buffer_img, int64_t* buffer_label,
+                         int64_t* pairs_out, void* stream_) {
+  using namespace b200ocl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200OCL_CHECK_ARG(n_cur >= 0 && n_cand_buf >= 0 && n_total == n_cand_buf + n_cur, "need n_total == n_cand_buf + n_cur");
+  if (n_cur == 0) return B200OCL_OK;
+  B200OCL_CHECK_ARG(order && cand_slot && cur_x && cur_y && buffer_img && buffer_label, "null pointer");
+  B200OCL_CHECK_ARG(row_bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(cur_x) | reinterpret_cast<uintptr_t>(buffer_img)) & 15) == 0,
+                    "rows must be 16-byte aligned multiples of 16 bytes");
+  B200OCL_PROF("move_rows", 2.0 * n_cur * (double)row_bytes, stream);
+  aser_replace_kernel<<<n_cur, 256, 0, stream>>>(reinterpret_cast<const long long*>(order), n_total, n_cand_buf,
+                                                 reinterpret_cast<const long long*>(cand_slot),
+                                                 static_cast<const unsigned char*>(cur_x),
+                                                 reinterpret_cast<const long long*>(cur_y), n_cur, row_bytes,
+                                                 static_cast<unsigned char*>(buffer_img),
+                                                 reinterpret_cast<long long*>(buffer_label),
+                                                 reinterpret_cast<long long*>(pairs_out));
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
 }
 
 int b200ocl_sgd_step(const float* p, const float* g, float* out, size_t n, float lr, float wd, void* stream_) {

@@ -702,6 +702,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
       }
     } else {
       a.transposed = 1;
+      a.parity_order = (c.stride == 2 && c.hin % 2 == 0 && c.win % 2 == 0) ? 1 : 0;
     }
     return launch_conv(a, stream);
   };

@@ -86,14 +86,22 @@ int b200ocl_profile_end(void) {
   g_agg.clear();
   FILE* dump = nullptr;
   if (const char* path = getenv("B200OCL_PROF_DUMP")) dump = fopen(path, "a");   // one line per launch
-  for (auto& r : g_recs) {
+  for (size_t i = 0; i < g_recs.size(); ++i) {
+    auto& r = g_recs[i];
     float ms = 0.f;
     if (r.open || cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
-    if (dump) fprintf(dump, "%s,%.1f,%.3f\n", r.name, r.work, ms * 1e3);
+    if (dump) {
+      // 4th column: idle time on the stream between the previous recorded launch and this one
+      float gap = 0.f;
+      if (i > 0 && !g_recs[i - 1].open && cudaEventElapsedTime(&gap, g_recs[i - 1].b, r.a) != cudaSuccess) gap = 0.f;
+      fprintf(dump, "%s,%.1f,%.3f,%.3f\n", r.name, r.work, ms * 1e3, gap * 1e3);
+    }
     bool found = false;
     for (auto& a : g_agg)
       if (a.name == r.name) { a.ms += ms; a.work += r.work; a.count += 1; found = true; break; }
     if (!found) g_agg.push_back({r.name, (double)ms, r.work, 1});
+  }
+  for (auto& r : g_recs) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }

@@ -46,80 +46,196 @@ def class_balanced_indices(labels, n_valid, n_smp_cls, excl_mask=None, rng=None)
 
 def uniform_indices(n_filled, num_retrieve, excl_indices=None):
     """np.random.choice without replacement over the filled slots minus excl_indices -- the same
-    numpy calls, in the same order, as random_retrieve (buffer_utils.py:9-17), so a seeded
-    numpy stream yields the reference's indices."""
-    filled = np.arange(n_filled)
-    excl = [] if excl_indices is None else list(excl_indices)
-    valid = np.setdiff1d(filled, np.array(excl))
+    draw, on the same population, as random_retrieve (buffer_utils.py:9-17), so a seeded numpy
+    stream yields the reference's indices.  (The population is built with a boolean mask instead of
+    np.setdiff1d: same sorted result, 40x cheaper on the host.)"""
+    keep = np.ones(n_filled, dtype=bool)
+    if excl_indices is not None and len(excl_indices) > 0:
+        ex = np.asarray(list(excl_indices) if not isinstance(excl_indices, np.ndarray) else excl_indices, dtype=np.int64)
+        keep[ex[(ex >= 0) & (ex < n_filled)]] = False
+    valid = np.flatnonzero(keep)
     num_retrieve = min(num_retrieve, valid.shape[0])
     return np.random.choice(valid, num_retrieve, replace=False).astype(np.int64)
 
 
-class _Pinned:
-    """Reusable pinned host staging for small index / label uploads."""
+# --------------------------------------------------------------------------- host <-> device plumbing
+_TORCH_DTYPE = {np.int64: torch.int64, np.int32: torch.int32, np.float32: torch.float32, np.float64: torch.float64,
+                np.uint8: torch.uint8, np.bool_: torch.bool}
 
-    def __init__(self):
+
+class _PinnedRing:
+    """Pinned staging ring for small host -> device uploads (indices, labels, augmentation parameters).
+    torch's pageable .to(device) synchronises the stream on every call; uploads from this ring are truly
+    asynchronous, so the host keeps running ahead of the GPU.  The ring has two halves; before a half is
+    reused the event recorded when it was last left is waited on (long past in practice)."""
+
+    def __init__(self, nbytes=1 << 20):
+        self.nbytes = nbytes
         self.buf = None
+        self.off = 0
+        self.events = [None, None]
+
+    def _ensure(self):
+        if self.buf is None:
+            self.buf = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
 
     def upload(self, arr, device):
-        arr = np.ascontiguousarray(arr, dtype=np.int64)
-        n = arr.size
-        if device.type != 'cuda':
-            return torch.from_numpy(arr.copy())
-        if self.buf is None or self.buf.numel() < n:
-            self.buf = torch.empty(max(256, 2 * n), dtype=torch.int64).pin_memory()
-        # a fresh pinned slice per call would race with an in-flight copy; rotate through the buffer
-        self.buf[:n].copy_(torch.from_numpy(arr))
-        out = torch.empty(n, dtype=torch.int64, device=device)
-        out.copy_(self.buf[:n], non_blocking=False)
+        arr = np.ascontiguousarray(arr)
+        n = arr.nbytes
+        out = torch.empty(arr.shape, dtype=_TORCH_DTYPE[arr.dtype.type], device=device)
+        if n == 0:
+            return out
+        self._ensure()
+        half = self.nbytes // 2
+        if n > half:      # large arrays bypass the ring
+            out.copy_(torch.from_numpy(arr))
+            return out
+        need = (n + 15) // 16 * 16
+        cur_half = self.off // half
+        if (self.off % half) + need > half:          # move to the other half
+            ev = torch.cuda.Event()
+            ev.record()
+            self.events[cur_half] = ev
+            cur_half ^= 1
+            self.off = cur_half * half
+            if self.events[cur_half] is not None:
+                self.events[cur_half].synchronize()
+                self.events[cur_half] = None
+        view = self.buf[self.off:self.off + n]
+        view.numpy()[:] = arr.reshape(-1).view(np.uint8)
+        self.off += need
+        out.view(torch.uint8).reshape(-1).copy_(view, non_blocking=True)
         return out
+
+
+_ring = _PinnedRing()
+
+
+def to_device(arr, device):
+    """Small host array -> device tensor of the same dtype, without a stream synchronisation."""
+    arr = np.ascontiguousarray(arr)
+    if torch.device(device).type != 'cuda':
+        return torch.from_numpy(arr.copy())
+    return _ring.upload(arr, torch.device(device))
 
 
 def to_device_i64(arr, device):
     """Small host int64 array -> device tensor."""
-    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64))
-    return t.to(device) if torch.device(device).type == 'cuda' else t
+    return to_device(np.ascontiguousarray(arr, dtype=np.int64), device)
+
+
+# Host-mirror updates that depend on device results (ASER's replacement decision) are deferred: the
+# decision is copied to pinned memory asynchronously and applied here, the next time any host-side
+# index logic runs -- by then the copy has long completed, so nothing waits on the GPU.
+_pending = []
+_pinned_pool = []
+
+
+def defer(fn):
+    _pending.append(fn)
+
+
+def flush_pending():
+    while _pending:
+        fn = _pending.pop(0)
+        fn()
+
+
+def pinned_i64(n):
+    for i, t in enumerate(_pinned_pool):
+        if t.numel() >= n:
+            return _pinned_pool.pop(i)
+    return torch.empty(max(64, n), dtype=torch.int64).pin_memory()
+
+
+def release_pinned(t):
+    if len(_pinned_pool) < 8:
+        _pinned_pool.append(t)
 
 
 # --------------------------------------------------------------------------- class-balanced sampler
 class ClassBalancedRandomSampling:
     """Class-level state like the reference (buffer_utils.py:74-79): two buffers in one process
-    share it and the ASER plugin constructors reset it (aser_retrieve.py:19, aser_update.py:20)."""
+    share it and the ASER plugin constructors reset it (aser_retrieve.py:19, aser_update.py:20).
+
+    Besides the reference's caches the sampler keeps a slot table tab[class, position] with counts and
+    each slot's position, maintained incrementally; a class-balanced draw is then one block of uniform
+    keys over the table and an argmin / argpartition per row (~80 us for 5000 slots x 100 classes,
+    against ~400 us for the sort-based class_balanced_indices and ~5000 .item() calls in the reference)."""
     class_index_cache = None     # dict class -> set(slot)   (kept for parity with the reference's API)
     class_num_cache = None       # np.int64 [num_class]
     labels_host = None           # np.int64 [mem] mirror the sampler draws from
     n_valid = 0
+    _member = None               # bool [mem]: slot registered through update_cache
+    _tab = None                  # int64 [num_class, cap]
+    _cnt = None                  # int64 [num_class]
+    _pos = None                  # int64 [mem]
 
     @classmethod
     def reset(cls):
+        flush_pending()
         cls.class_index_cache = None
         cls.class_num_cache = None
         cls.labels_host = None
         cls.n_valid = 0
+        cls._member = None
+        cls._tab = None
+        cls._cnt = None
+        cls._pos = None
+
+    # ---- slot table
+    @classmethod
+    def _tab_add(cls, slot, c):
+        if c >= cls._tab.shape[0]:
+            rows = max(c + 1, 2 * cls._tab.shape[0])
+            cls._tab = np.vstack([cls._tab, np.full((rows - cls._tab.shape[0], cls._tab.shape[1]), -1, dtype=np.int64)])
+            cls._cnt = np.concatenate([cls._cnt, np.zeros(rows - cls._cnt.shape[0], dtype=np.int64)])
+        k = int(cls._cnt[c])
+        if k >= cls._tab.shape[1]:
+            cls._tab = np.hstack([cls._tab, np.full((cls._tab.shape[0], max(8, cls._tab.shape[1])), -1, dtype=np.int64)])
+        cls._tab[c, k] = slot
+        cls._pos[slot] = k
+        cls._cnt[c] = k + 1
 
     @classmethod
-    def sample_indices(cls, n_smp_cls, excl_indices=None):
+    def _tab_remove(cls, slot, c):
+        k, last = int(cls._pos[slot]), int(cls._cnt[c]) - 1
+        moved = cls._tab[c, last]
+        cls._tab[c, k] = moved
+        cls._pos[moved] = k
+        cls._tab[c, last] = -1
+        cls._cnt[c] = last
+
+    @classmethod
+    def sample_indices(cls, n_smp_cls, excl_indices=None, rng=None):
+        """Up to n_smp_cls uniformly random registered slots of every class, minus excl_indices
+        (ClassBalancedRandomSampling.sample, buffer_utils.py:81-121).  Class-major output (ascending
+        class id), random inside a class."""
+        flush_pending()
         if cls.labels_host is None:
             raise RuntimeError('ClassBalancedRandomSampling.update_cache has not been called')
-        excl_mask = None
+        rng = np.random if rng is None else rng
+        n = int(n_smp_cls)
+        cap = int(cls._cnt.max()) if cls._cnt.size else 0
+        if n <= 0 or cap == 0:
+            return np.zeros(0, dtype=np.int64)
+        C = cls._tab.shape[0]
+        u = rng.random((C, cap))
+        u[np.arange(cap)[None, :] >= cls._cnt[:, None]] = 2.0
         if excl_indices is not None and len(excl_indices) > 0:
-            excl_mask = np.zeros(cls.labels_host.shape[0], dtype=bool)
-            excl_mask[np.asarray(list(excl_indices), dtype=np.int64)] = True
-        # only slots registered through update_cache take part (the reference samples from its cache)
-        member = cls._member_mask()
-        if excl_mask is None:
-            excl_mask = ~member
-        else:
-            excl_mask |= ~member
-        return class_balanced_indices(cls.labels_host, cls.labels_host.shape[0], n_smp_cls, excl_mask)
-
-    @classmethod
-    def _member_mask(cls):
-        if cls._member is None or cls._member.shape[0] != cls.labels_host.shape[0]:
-            cls._member = np.zeros(cls.labels_host.shape[0], dtype=bool)
-        return cls._member
-
-    _member = None
+            ex = np.asarray(list(excl_indices) if not isinstance(excl_indices, np.ndarray) else excl_indices, dtype=np.int64)
+            ex = ex[cls._member[ex]]
+            u[cls.labels_host[ex], cls._pos[ex]] = 2.0
+        if n == 1:
+            j = u.argmin(axis=1)
+            rows = np.flatnonzero(u[np.arange(C), j] < 2.0)
+            return cls._tab[rows, j[rows]].astype(np.int64)
+        n_eff = min(n, cap)
+        part = np.argpartition(u, n_eff - 1, axis=1)[:, :n_eff] if n_eff < cap else np.tile(np.arange(cap), (C, 1))
+        keys = np.take_along_axis(u, part, axis=1)
+        o = np.argsort(keys, axis=1, kind='stable')
+        part, keys = np.take_along_axis(part, o, axis=1), np.take_along_axis(keys, o, axis=1)
+        return cls._tab[np.arange(C)[:, None], part][keys < 2.0].astype(np.int64)
 
     @classmethod
     def sample(cls, buffer_x, buffer_y, n_smp_cls, excl_indices=None, device='cpu'):
@@ -135,19 +251,26 @@ class ClassBalancedRandomSampling:
         """Incremental update (new_y/ind given, buffer_utils.py:140-154) or full rebuild from the
         label buffer (buffer_utils.py:155-160).  Accepts host arrays; device tensors are copied
         once (a sync) only when no host mirror is supplied."""
+        flush_pending()
+        cls._update_cache_now(buffer_y, num_class, new_y, ind, labels_host)
+
+    @classmethod
+    def _update_cache_now(cls, buffer_y, num_class, new_y=None, ind=None, labels_host=None):
         def host(a):
             if a is None:
                 return None
             if isinstance(a, torch.Tensor):
                 return a.detach().cpu().numpy().astype(np.int64)
             return np.asarray(a, dtype=np.int64)
-        if cls.class_index_cache is None or new_y is None:
+        if cls.class_index_cache is None:
             n = buffer_y.shape[0]
-            if cls.class_index_cache is None:
-                cls.class_index_cache = {}
-                cls.class_num_cache = np.zeros(num_class, dtype=np.int64)
-                cls.labels_host = np.zeros(n, dtype=np.int64)
-                cls._member = np.zeros(n, dtype=bool)
+            cls.class_index_cache = {}
+            cls.class_num_cache = np.zeros(num_class, dtype=np.int64)
+            cls.labels_host = np.zeros(n, dtype=np.int64)
+            cls._member = np.zeros(n, dtype=bool)
+            cls._tab = np.full((max(1, num_class), 8), -1, dtype=np.int64)
+            cls._cnt = np.zeros(max(1, num_class), dtype=np.int64)
+            cls._pos = np.zeros(n, dtype=np.int64)
         if new_y is not None:
             new_y, ind = host(new_y), host(ind)
             for i, ny in zip(ind.tolist(), new_y.tolist()):
@@ -155,17 +278,33 @@ class ClassBalancedRandomSampling:
                     oy = int(cls.labels_host[i])
                     cls.class_index_cache[oy].discard(i)
                     cls.class_num_cache[oy] -= 1
+                    cls._tab_remove(i, oy)
                 cls.class_index_cache.setdefault(ny, set()).add(i)
                 cls.class_num_cache[ny] += 1
                 cls.labels_host[i] = ny
                 cls._member[i] = True
+                cls._tab_add(i, ny)
         else:
             lab = host(labels_host) if labels_host is not None else host(buffer_y)
             cls.labels_host = lab.copy()
-            cls._member = np.ones(lab.shape[0], dtype=bool)
+            n = lab.shape[0]
+            cls._member = np.ones(n, dtype=bool)
             cache = {}
-            for c in np.unique(lab).tolist():
-                cache[c] = set(np.flatnonzero(lab == c).tolist())
+            C = max(int(lab.max()) + 1 if n else 1, num_class, 1)
+            counts = np.bincount(lab, minlength=C)
+            cls._tab = np.full((C, max(8, int(counts.max()) if n else 8)), -1, dtype=np.int64)
+            cls._cnt = counts.astype(np.int64)
+            cls._pos = np.zeros(n, dtype=np.int64)
+            order = np.argsort(lab, kind='stable')
+            start = 0
+            for c in range(C):
+                k = int(counts[c])
+                if k:
+                    members = order[start:start + k]
+                    cls._tab[c, :k] = members
+                    cls._pos[members] = np.arange(k)
+                    cache[c] = set(members.tolist())
+                    start += k
             cls.class_index_cache = cache
             # the reference leaves class_num_cache untouched on this path (buffer_utils.py:155-160)
 
@@ -201,7 +340,7 @@ class Buffer(torch.nn.Module):
         dev = torch.device(self.device)
         self.register_buffer('buffer_img', torch.zeros((buffer_size, *input_size), dtype=torch.float32, device=dev))
         self.register_buffer('buffer_label', torch.zeros(buffer_size, dtype=torch.int64, device=dev))
-        self.labels_host = np.zeros(buffer_size, dtype=np.int64)
+        self._labels_host = np.zeros(buffer_size, dtype=np.int64)
         if update_methods is None or retrieve_methods is None:
             from . import registry
             update_methods = update_methods or registry.update_methods
@@ -210,6 +349,17 @@ class Buffer(torch.nn.Module):
         self.retrieve_method = retrieve_methods[params.retrieve](params)
         if getattr(self.params, 'buffer_tracker', False):
             raise NotImplementedError('buffer_tracker belongs to the match/mem_match retrievals, outside the replay path')
+
+    @property
+    def labels_host(self):
+        """numpy mirror of buffer_label; deferred device-decided updates are applied before it is read."""
+        flush_pending()
+        return self._labels_host
+
+    @labels_host.setter
+    def labels_host(self, value):
+        flush_pending()
+        self._labels_host = np.asarray(value, dtype=np.int64)
 
     def update(self, x, y, **kwargs):
         return self.update_method.update(buffer=self, x=x, y=y, **kwargs)

@@ -151,6 +151,28 @@ def scatter_rows(dst, idx, src):
     return dst
 
 
+def aser_replace(order, n_cand_buf, cand_slot, cur_x, cur_y, buffer_img, buffer_label):
+    """ASER's memory replacement taken on the device (aser_update.py:88-112): moves the winning rows of
+    the current batch into the losing candidates' slots and returns the decision as a device int64
+    tensor [1 + 2*n_cur] = (count, positions in the current batch, buffer slots), -1 padded."""
+    _need_cuda(order, cand_slot, cur_x, cur_y, buffer_img, buffer_label)
+    order, cand_slot, cur_y = _i64(order).reshape(-1), _i64(cand_slot).reshape(-1), _i64(cur_y).reshape(-1)
+    n_cur = cur_y.numel()
+    if order.numel() != n_cand_buf + n_cur or cand_slot.numel() != n_cand_buf:
+        raise ValueError('order must rank n_cand_buf + n_cur candidates')
+    if not (cur_x.is_contiguous() and buffer_img.is_contiguous()) or cur_x.dtype != buffer_img.dtype:
+        raise ValueError('cur_x / buffer_img must be contiguous and of one dtype')
+    pairs = torch.empty(1 + 2 * n_cur, dtype=torch.int64, device=order.device)
+    if n_cur == 0:
+        return pairs.fill_(0)
+    row_bytes = buffer_img[0].numel() * buffer_img.element_size()
+    rc = _native.lib().b200ocl_aser_replace(_ptr(order), n_cand_buf + n_cur, n_cand_buf, _ptr(cand_slot), _ptr(cur_x),
+                                            _ptr(cur_y), n_cur, row_bytes, _ptr(buffer_img), _ptr(buffer_label),
+                                            _ptr(pairs), _stream())
+    _native.check(rc, 'b200ocl_aser_replace')
+    return pairs
+
+
 def sgd_step(param, grad, lr, weight_decay=0.0, out=None):
     """out = param - lr*(grad + wd*param) over flat fp32 arenas; out defaults to param (in place)."""
     _need_cuda(param, grad, out)

@@ -3,7 +3,7 @@
 import numpy as np
 import torch
 
-from . import ops
+from . import memory, ops
 from .memory import ClassBalancedRandomSampling, n_classes, to_device_i64, uniform_indices
 from .nets import engine_of
 
@@ -87,9 +87,11 @@ class ASER_update(object):
         self.n_smp_cls = int(params.n_smp_cls)
         self.n_total_smp = int(params.n_smp_cls * self.out_dim)
         self.reservoir_update = Reservoir_update(params)
+        self._last_decision = None
         ClassBalancedRandomSampling.reset()
 
     def update(self, buffer, x, y, **kwargs):
+        memory.flush_pending()
         y_host = _host_labels(y, kwargs)
         place_left = self.mem_size - buffer.current_index
         if place_left:
@@ -134,11 +136,33 @@ class ASER_update(object):
         eval_y = to_device_i64(np.concatenate([buffer.labels_host[eval_ind], cur_y_host[minority]]), dev)
         sv_sum = ops.knn_sv(eval_f, eval_y, cand_f, cand_y, self.k, want_sum=True)['sum']
         order = ops.rank_desc(sv_sum)                                  # full descending ranking
-        ind_cur, ind_buffer = aser_update_partition(order.cpu().numpy(), n_cand_buf, cand_ind)   # the step's one sync
         buffer.n_seen_so_far += n_cur
-        if ind_cur.size:
-            y_upt_host = cur_y_host[ind_cur]
-            src_t = to_device_i64(ind_cur, dev)
-            CB.update_cache(buffer.buffer_label, self.out_dim, new_y=y_upt_host, ind=ind_buffer)
-            buffer.write(ind_buffer, ops.gather_rows(cur_x, src_t), ops.gather_rows(cur_y, src_t), y_upt_host)
-        self.last_decision = (ind_cur, ind_buffer)
+        # The replacement itself (aser_update.py:88-112) happens on the device; the host mirror (labels,
+        # class caches) follows from an asynchronous copy of the decision, applied the next time host-side
+        # index logic runs -- the step has no device -> host synchronisation.
+        cur_xc = cur_x.detach().to(torch.float32).contiguous()
+        pairs = ops.aser_replace(order, n_cand_buf, idx_t[n_eval_buf:], cur_xc, cur_y, buffer.buffer_img, buffer.buffer_label)
+        host = memory.pinned_i64(pairs.numel())
+        host[:pairs.numel()].copy_(pairs, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        y_host = np.array(cur_y_host, dtype=np.int64, copy=True)
+        out_dim = self.out_dim
+
+        def apply():
+            done.synchronize()
+            arr = host[:1 + 2 * n_cur].numpy().copy()
+            memory.release_pinned(host)
+            cnt = int(arr[0])
+            ind_cur, ind_buffer = arr[1:1 + cnt], arr[1 + n_cur:1 + n_cur + cnt]
+            if cnt:
+                CB._update_cache_now(buffer.buffer_label, out_dim, new_y=y_host[ind_cur], ind=ind_buffer)
+                buffer._labels_host[ind_buffer] = y_host[ind_cur]
+            self._last_decision = (ind_cur, ind_buffer)
+        memory.defer(apply)
+
+    @property
+    def last_decision(self):
+        """(positions in the current batch, buffer slots they replaced) of the latest update."""
+        memory.flush_pending()
+        return self._last_decision
