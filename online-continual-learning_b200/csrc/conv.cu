@@ -748,8 +748,20 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     set_error("launch_conv: channel counts must be multiples of 20 (CK=%d CN=%d M=%d)", a.CK, a.CN, a.M);
     return B200OCL_EUNSUPPORTED;
   }
-  // 3x3 stride-1 convolutions with enough 128-pixel tiles run on the tensor cores (conv_tc.cu).
-  if (conv_tc_eligible(a)) return launch_conv_tc(a, stream);
+  // 3x3 stride-1 convolutions on 8/16/32-wide maps: tensor cores fed from a halo patch (conv_tcp.cu);
+  // other 3x3 stride-1 shapes with enough 128-pixel tiles: tensor cores with an im2col tile (conv_tc.cu).
+  if (a.force_path == 3) {
+    if (!conv_tcp_eligible(a)) { set_error("launch_conv: shape not covered by the halo-patch tensor-core kernel"); return B200OCL_EUNSUPPORTED; }
+    return launch_conv_tcp(a, stream);
+  }
+  if (a.force_path == 2) {
+    if (!(a.w_tc && a.ks == 3 && a.stride == 1 && !a.transposed)) { set_error("launch_conv: shape not covered by conv_tc"); return B200OCL_EUNSUPPORTED; }
+    return launch_conv_tc(a, stream);
+  }
+  if (a.force_path == 0) {
+    if (conv_tcp_eligible(a)) return launch_conv_tcp(a, stream);
+    if (conv_tc_eligible(a)) return launch_conv_tc(a, stream);
+  }
   // Forward convolutions and stride-1 data gradients with enough pixels go to the patch kernel:
   // pick the widest channel tile and 2 pixels per thread that still give >= 3 CTAs per SM.
   if (!a.transposed && a.ks * a.ks * 20 * 80 * sizeof(float) <= 64 * 1024) {

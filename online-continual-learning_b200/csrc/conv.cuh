@@ -22,6 +22,9 @@ struct ConvArgs {
                      //    (input pixel (t/stride) with t = ho + pad - kh, only when divisible)
   const float* w_tc; // tensor-core operand image of the same weights (net_plan.cuh), nullable
   int tc_kb, tc_bn;  // its K blocks and real channels per tile
+  const float* w_tp; // halo-patch tensor-core image (conv_tcp.cu), nullable
+  int tp_bn, tp_slices;
+  int force_path;    // 0 automatic; 1 CUDA-core kernels only; 2 conv_tc; 3 conv_tcp (selftest: fails if not eligible)
   int parity_order;  // stride-2 data gradient only: pixels enumerated [parity class][n][h/2][w/2] so that a CTA
                      //    sees one class and skips the taps that cannot reach it (9 of 36 tap-pixel pairs are live)
   int flip;          // patch kernel only: use tap (ks*ks-1-tap) of the weights (stride-1 data gradient)
@@ -51,6 +54,8 @@ int conv_max_grid_m(int M);
 int launch_conv(const ConvArgs& a, cudaStream_t stream);   // CK, CN multiples of 20
 int launch_stem(const ConvArgs& a, cudaStream_t stream);
 int launch_conv_tc(const ConvArgs& a, cudaStream_t stream);  // conv_tc.cu: tcgen05 3xTF32 path
-bool conv_tc_eligible(const ConvArgs& a);   // CK == 3, CN == 20, ks == 3, NCHW input
+bool conv_tc_eligible(const ConvArgs& a);
+int launch_conv_tcp(const ConvArgs& a, cudaStream_t stream);  // conv_tcp.cu: tcgen05 fed from a halo patch
+bool conv_tcp_eligible(const ConvArgs& a);   // CK == 3, CN == 20, ks == 3, NCHW input
 
 }  // namespace b200ocl

@@ -1,0 +1,463 @@
+// conv_tcp.cu -- 3x3 stride-1 convolution on tcgen05 fed IN PLACE from a halo patch (sm_100a).
+//
+// conv_tc.cu builds an im2col tile per K block: every output pixel re-gathers, re-splits and re-stores
+// its input 9 times, and that staging chain -- not the tensor core -- is what a K block costs.  Here the
+// input patch of a tile (with its halo) is staged ONCE per 32-channel slice as two 128-byte-swizzled
+// arrays (TF32 hi / lo) of one 128-byte row per patch pixel, and the A operand of every tap is that
+// same array read through a shifted shared-memory descriptor:
+//
+//   tile   = 8 (w) x 16 (h) output pixels of one image   (or 8 x 8 of two images when H = 8)
+//   patch  = 18 x 10 pixels (20 x 10 with two interleaved images), row index P*10 + c, 128 B each
+//   MMA row 8g + r = output pixel (row g, column r)  ->  patch row (g + kh) * 10 + (r + kw)
+//          = descriptor start  base + (kh*10 + kw) * 128,  8-row groups 10 rows (1280 B) apart.
+//
+// The hardware applies the 128-byte swizzle to absolute address bits, so a window that starts at any
+// 128-byte row of a patch stored with "chunk ^= row & 7" reads back exactly (tests/test_gpu_umma.py,
+// b200ocl_selftest_umma_window: every start row and an SBO of 10 rows, base-offset field 0).
+//
+// Per tile and slice the tensor core runs 9 taps x ceil(channels/8) K steps x 3 MMAs (3xTF32:
+// hi*hi + hi*lo + lo*hi); each tap accumulates into its own TMEM buffer which the promotion warps
+// add into fp32 registers (a long TMEM accumulation truncates, see conv_tc.cu).  Roles:
+//   warps 0-3  promotion + epilogue (TMEM lane quarter = warp), folded eval BN / raw + batch statistics
+//   warp  4    MMA issue (one thread), TMEM allocation
+//   warp  5    weight loader (one thread): cp.async.bulk of pre-split, pre-swizzled [NT x 32] tiles,
+//              resident for the whole kernel when all 9 taps fit (cin <= 32), a 4-deep ring otherwise
+//   warps 6-9  patch loaders: coalesced LDG.128 of NHWC pixels, cvt.rna.tf32 split, swizzled stores
+// CTAs are persistent over pixel tiles (one CTA per SM); batch statistics are accumulated per CTA in
+// fp64 in a fixed order and finalised by the last CTA (deterministic, as everywhere else).
+#include <stdlib.h>
+
+#include "conv.cuh"
+#include "umma.cuh"
+
+namespace b200ocl {
+namespace {
+
+constexpr int TP_THREADS = 320;
+constexpr int TP_PROWS = 200;                       // patch rows allocated per stage (180 or 200 used)
+constexpr int TP_PATCH_BYTES = TP_PROWS * 128;      // one of hi / lo
+constexpr int TP_PS = 2;                            // patch stages
+constexpr int TP_NB = 4;                            // TMEM accumulator buffers
+constexpr int TP_BS = 4;                            // weight ring depth (streaming mode)
+constexpr int TP_LD_MAX = 13;                       // 16-byte chunks a loader thread stages per patch (1600 / 128)
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(umma::smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+          umma::smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(umma::smem_u32(bar))
+      : "memory");
+}
+
+template <int NT>
+__device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NT]) {
+#pragma unroll
+  for (int c0 = 0; c0 < NT; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[c0 + j] += v[j];
+  }
+}
+
+struct TileGeom {
+  int tiles_w, tiles_h, ipt, khs, prow;   // tiles per image row / column, images per tile, patch rows per kh, patch rows
+  int tiles_m;
+};
+__host__ __device__ inline TileGeom tile_geom(int N, int H, int W) {
+  TileGeom g;
+  g.tiles_w = W / 8;
+  g.ipt = (H == 8) ? 2 : 1;
+  g.tiles_h = (g.ipt == 2) ? 1 : H / 16;
+  g.khs = 10 * g.ipt;
+  g.prow = (g.ipt == 2) ? 20 : 18;
+  g.tiles_m = ((N + g.ipt - 1) / g.ipt) * g.tiles_h * g.tiles_w;
+  return g;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
+  constexpr uint32_t TMEM_COLS = (TP_NB * NT <= 128) ? 128 : ((TP_NB * NT <= 256) ? 256 : 512);
+  constexpr int B_BLOCK = 2 * NT * 32;   // floats: hi tile then lo tile
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* patch0 = smem_raw;                                          // [PS][hi | lo][PROWS][128 B]
+  float* sB = reinterpret_cast<float*>(smem_raw + TP_PS * 2 * TP_PATCH_BYTES);   // weight blocks
+  __shared__ __align__(8) uint64_t pfull[TP_PS], pempty[TP_PS], bfull[9], bempty[TP_BS], tfull[TP_NB], tempty[TP_NB];
+  __shared__ uint32_t tmem_slot;
+  __shared__ bool is_last;
+  __shared__ int s_fail;
+  __shared__ float s_coef[3 * 80];   // eval BN: mean, scale, shift per channel of the tile
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bn = a.tp_bn;
+  const int n0 = blockIdx.y * bn;
+  const int slices = a.tp_slices;
+  const TileGeom G = tile_geom(a.N, a.Hin, a.Win);
+  const bool resident = (slices == 1 && NT == 32);   // all 9 weight blocks stay in shared memory
+  const int b_slots = resident ? 9 : TP_BS;
+  float* s_t = sB + (size_t)b_slots * B_BLOCK;  // [128][bn + 1] transpose scratch for the batch statistics
+
+  if (warp == 4) umma::tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (tid == 0) {
+    for (int i = 0; i < TP_PS; ++i) {
+      umma::mbar_init(&pfull[i], 128);
+      umma::mbar_init(&pempty[i], 1);
+    }
+    for (int i = 0; i < 9; ++i) umma::mbar_init(&bfull[i], 1);
+    for (int i = 0; i < TP_BS; ++i) umma::mbar_init(&bempty[i], 1);
+    for (int i = 0; i < TP_NB; ++i) {
+      umma::mbar_init(&tfull[i], 1);
+      umma::mbar_init(&tempty[i], 128);
+    }
+    umma::fence_mbar_init();
+    s_fail = 0;
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = tmem_slot;
+  const float* wimg = a.w_tp + (size_t)blockIdx.y * slices * 9 * B_BLOCK;
+
+  if (warp >= 6) {
+    // =========================================================== patch loaders (128 threads)
+    const int lt = tid - 192;
+    int pc = 0;
+    for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
+      const int tw = tile % G.tiles_w;
+      const int th = (tile / G.tiles_w) % G.tiles_h;
+      const int ig = tile / (G.tiles_w * G.tiles_h);
+      for (int sl = 0; sl < slices; ++sl, ++pc) {
+        const int ch_valid = min(32, a.CK - sl * 32);       // real channels in this slice (multiple of 4)
+        const int nch = 2 * ((ch_valid + 7) / 8);            // 16-byte chunks the MMAs will read per row
+        const int ntask = G.prow * 10 * nch;
+        float4 v[TP_LD_MAX];
+#pragma unroll
+        for (int i = 0; i < TP_LD_MAX; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int task = lt + i * 128;
+          if (task < ntask) {
+            const int ri = task / nch, ch = task - ri * nch;
+            const int P = ri / 10, c = ri - P * 10;
+            int img, y;
+            if (G.ipt == 2) {
+              img = ig * 2 + (P & 1);
+              y = (P >> 1) - 1;
+            } else {
+              img = ig;
+              y = th * 16 + P - 1;
+            }
+            const int x = tw * 8 + c - 1;
+            if (img < a.N && (unsigned)y < (unsigned)a.Hin && (unsigned)x < (unsigned)a.Win && ch * 4 < ch_valid)
+              v[i] = __ldg(reinterpret_cast<const float4*>(a.in + ((size_t)(img * a.Hin + y) * a.Win + x) * a.CK + sl * 32) + ch);
+          }
+        }
+        const int ps = pc % TP_PS;
+        if (!umma::mbar_wait(&pempty[ps], (uint32_t)(((pc / TP_PS) & 1) ^ 1))) s_fail = 1;
+        float* ph = reinterpret_cast<float*>(patch0 + (size_t)ps * 2 * TP_PATCH_BYTES);
+        float* pl = ph + TP_PATCH_BYTES / 4;
+#pragma unroll
+        for (int i = 0; i < TP_LD_MAX; ++i) {
+          const int task = lt + i * 128;
+          if (task < ntask) {
+            const int ri = task / nch, ch = task - ri * nch;
+            float4 h, l;
+            umma::split_tf32(v[i].x, h.x, l.x); umma::split_tf32(v[i].y, h.y, l.y);
+            umma::split_tf32(v[i].z, h.z, l.z); umma::split_tf32(v[i].w, h.w, l.w);
+            const int off = umma::sw128_offset_f32(ri, ch);
+            *reinterpret_cast<float4*>(ph + off) = h;
+            *reinterpret_cast<float4*>(pl + off) = l;
+          }
+        }
+        umma::fence_proxy_async_smem();
+        umma::mbar_arrive(&pfull[ps]);
+      }
+    }
+  } else if (warp == 5) {
+    // =========================================================== weight loader (one elected lane)
+    const uint32_t bytes = (uint32_t)(B_BLOCK * sizeof(float));
+    if (resident) {
+      if (umma::elect_one_sync()) {
+        for (int b = 0; b < 9; ++b) {
+          mbar_expect_tx(&bfull[b], bytes);
+          bulk_g2s(sB + (size_t)b * B_BLOCK, wimg + (size_t)b * B_BLOCK, bytes, &bfull[b]);
+        }
+      }
+    } else {
+      int q = 0;
+      for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x)
+        for (int sl = 0; sl < slices; ++sl)
+          for (int tap = 0; tap < 9; ++tap, ++q) {
+            const int bs = q % TP_BS;
+            if (!umma::mbar_wait(&bempty[bs], (uint32_t)(((q / TP_BS) & 1) ^ 1))) s_fail = 1;
+            if (umma::elect_one_sync()) {
+              mbar_expect_tx(&bfull[bs], bytes);
+              bulk_g2s(sB + (size_t)bs * B_BLOCK, wimg + (size_t)(sl * 9 + tap) * B_BLOCK, bytes, &bfull[bs]);
+            }
+            __syncwarp();
+          }
+    }
+  } else if (warp == 4) {
+    // =========================================================== MMA issuer (whole warp waits, one elected lane issues)
+    const uint32_t idesc = umma::make_idesc_tf32(128, NT);
+    const uint64_t sbo_fix = ((uint64_t)((1280 >> 4) & 0x3FFF)) << 32;   // 8-row groups are 10 patch rows apart
+    // descriptor templates: only the 14-bit start-address field (16-byte units) changes per stage / tap / K step
+    const uint64_t dA0 = (umma::make_smem_desc_sw128(umma::smem_u32(patch0)) & ~((uint64_t)0x3FFF << 32)) | sbo_fix;
+    const uint64_t dB0 = umma::make_smem_desc_sw128(umma::smem_u32(sB));
+    constexpr uint32_t A_LO = TP_PATCH_BYTES >> 4;           // hi -> lo patch, 16-byte units
+    constexpr uint32_t A_STAGE = (2 * TP_PATCH_BYTES) >> 4;
+    constexpr uint32_t B_LO = (NT * 128) >> 4;
+    constexpr uint32_t B_SLOT = (B_BLOCK * 4) >> 4;
+    int q = 0, pc = 0;
+    for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
+      for (int sl = 0; sl < slices; ++sl, ++pc) {
+        const int ps = pc % TP_PS;
+        const int ksteps = (min(32, a.CK - sl * 32) + 7) / 8;
+        if (!umma::mbar_wait(&pfull[ps], (uint32_t)((pc / TP_PS) & 1))) s_fail = 1;
+        const uint64_t dAs = dA0 + (uint64_t)(ps * A_STAGE);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap, ++q) {
+          const int b = resident ? tap : q % TP_BS;   // resident: slices == 1, block index = tap
+          const int t = q % TP_NB;
+          if (!umma::mbar_wait(&bfull[b], resident ? 0u : (uint32_t)((q / TP_BS) & 1))) s_fail = 1;
+          if (!umma::mbar_wait(&tempty[t], (uint32_t)(((q / TP_NB) & 1) ^ 1))) s_fail = 1;
+          umma::fence_after_thread_sync();
+          const int kh = tap / 3, kw = tap - kh * 3;
+          const uint64_t dAh = dAs + (uint64_t)((kh * G.khs + kw) * 8);   // 128 bytes per patch row
+          const uint64_t dAl = dAh + A_LO;
+          const uint64_t dBh = dB0 + (uint64_t)(b * B_SLOT);
+          const uint64_t dBl = dBh + B_LO;
+          const uint32_t dcol = tmem + (uint32_t)(t * NT);
+          if (umma::elect_one_sync()) {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);   // 32 bytes per K step, in 16-byte units
+              umma::mma_tf32_ss(dcol, dAh + adv, dBh + adv, idesc, k > 0 ? 1u : 0u);
+              umma::mma_tf32_ss(dcol, dAh + adv, dBl + adv, idesc, 1u);
+              umma::mma_tf32_ss(dcol, dAl + adv, dBh + adv, idesc, 1u);
+            }
+            if (!resident) umma::mma_commit(&bempty[b]);
+            umma::mma_commit(&tfull[t]);
+            if (tap == 8) umma::mma_commit(&pempty[ps]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // =========================================================== promotion + epilogue (warps 0-3)
+    const int et = tid;                        // 0..127 = MMA row = TMEM lane
+    const uint32_t my_lanes = tmem + ((uint32_t)(warp * 32) << 16);
+    auto esync = []() { asm volatile("bar.sync 1, 128;\n" ::); };
+    if (a.mode == CONV_EVAL) {
+      for (int c = et; c < bn; c += 128) {
+        const float inv = 1.0f / sqrtf(a.rvar[n0 + c] + a.eps);
+        s_coef[c] = a.rmean[n0 + c];
+        s_coef[80 + c] = inv * a.gamma[n0 + c];
+        s_coef[160 + c] = a.beta[n0 + c];
+      }
+      esync();
+    }
+    const int g = et >> 3, r = et & 7;
+    double statS = 0.0, statQ = 0.0;           // thread c < bn: running sums of channel c over this CTA's tiles
+    int q = 0;
+    for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
+      const int tw = tile % G.tiles_w;
+      const int th = (tile / G.tiles_w) % G.tiles_h;
+      const int ig = tile / (G.tiles_w * G.tiles_h);
+      float acc[NT];
+#pragma unroll
+      for (int c = 0; c < NT; ++c) acc[c] = 0.f;
+      for (int kb = 0; kb < slices * 9; ++kb, ++q) {
+        const int t = q % TP_NB;
+        if (!umma::mbar_wait(&tfull[t], (uint32_t)((q / TP_NB) & 1))) s_fail = 1;
+        umma::fence_after_thread_sync();
+        tmem_accumulate<NT>(my_lanes + (uint32_t)(t * NT), acc);
+        umma::fence_before_thread_sync();
+        umma::mbar_arrive(&tempty[t]);
+      }
+      int img, y;
+      if (G.ipt == 2) {
+        img = ig * 2 + (g & 1);
+        y = g >> 1;
+      } else {
+        img = ig;
+        y = th * 16 + g;
+      }
+      const int x = tw * 8 + r;
+      const bool valid = img < a.N;
+      const size_t m = ((size_t)img * a.Hout + y) * a.Wout + x;
+      if (a.mode == CONV_EVAL) {
+        if (valid) {
+          float* o = a.out + m * a.CN + n0;
+          const float* rs = a.residual ? a.residual + m * a.CN + n0 : nullptr;
+#pragma unroll
+          for (int c0 = 0; c0 < NT; c0 += 4) {
+            if (c0 >= bn) break;
+            float rr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              rr[j] = (acc[c0 + j] - s_coef[c0 + j]) * s_coef[80 + c0 + j] + s_coef[160 + c0 + j];
+            if (rs) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rs + c0);
+              rr[0] += r4.x; rr[1] += r4.y; rr[2] += r4.z; rr[3] += r4.w;
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rr[j] = fmaxf(rr[j], 0.f);
+            }
+            *reinterpret_cast<float4*>(o + c0) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+          }
+        }
+      } else {
+        if (valid) {
+          float* o = a.out + m * a.CN + n0;
+#pragma unroll
+          for (int c0 = 0; c0 < NT; c0 += 4) {
+            if (c0 >= bn) break;
+            float4 rr = make_float4(acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]);
+            if (a.mode == CONV_ACCUM) {
+              const float4 old = *reinterpret_cast<const float4*>(o + c0);
+              rr.x += old.x; rr.y += old.y; rr.z += old.z; rr.w += old.w;
+            }
+            *reinterpret_cast<float4*>(o + c0) = rr;
+          }
+        }
+        if (a.mode == CONV_TRAIN) {
+          // transpose through shared memory; thread c sums its channel over the 128 rows in row order
+          // (rows of missing images hold exact zeros)
+#pragma unroll
+          for (int c = 0; c < NT; ++c)
+            if (c < bn) s_t[et * (bn + 1) + c] = acc[c];
+          esync();
+          if (et < bn) {
+            double S = 0.0, Q = 0.0;
+            for (int rr = 0; rr < 128; ++rr) {
+              const double xv = (double)s_t[rr * (bn + 1) + et];
+              S += xv;
+              Q += xv * xv;
+            }
+            statS += S;
+            statQ += Q;
+          }
+          esync();
+        }
+      }
+    }
+    if (a.mode == CONV_TRAIN) {
+      if (et < bn) {
+        double* dst = a.stat_part + ((size_t)blockIdx.x * a.CN + n0 + et) * 2;
+        dst[0] = statS;
+        dst[1] = statQ;
+      }
+      __threadfence();
+      esync();
+      if (et == 0) is_last = (atomicAdd(a.counter + blockIdx.y, 1u) == gridDim.x - 1);
+      esync();
+      if (is_last) {
+        __threadfence();
+        const int groups = 128 / bn;
+        const int ch = et % bn, grp = et / bn;
+        double* s_fin = reinterpret_cast<double*>(s_t);   // [groups][bn][2]
+        if (grp < groups) {
+          double S = 0.0, Q = 0.0;
+          unsigned int b = grp;
+          for (; b + 3 * groups < gridDim.x; b += 4 * groups) {
+            double2 pv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              pv[u] = __ldcg(reinterpret_cast<const double2*>(a.stat_part + ((size_t)(b + u * groups) * a.CN + n0 + ch) * 2));
+            S += (pv[0].x + pv[1].x) + (pv[2].x + pv[3].x);
+            Q += (pv[0].y + pv[1].y) + (pv[2].y + pv[3].y);
+          }
+          for (; b < gridDim.x; b += groups) {
+            const double2 pv = __ldcg(reinterpret_cast<const double2*>(a.stat_part + ((size_t)b * a.CN + n0 + ch) * 2));
+            S += pv.x;
+            Q += pv.y;
+          }
+          s_fin[(grp * bn + ch) * 2 + 0] = S;
+          s_fin[(grp * bn + ch) * 2 + 1] = Q;
+        }
+        esync();
+        if (et < bn) {
+          double Sm = 0.0, Q = 0.0;
+          for (int gq = 0; gq < groups; ++gq) {
+            Sm += s_fin[(gq * bn + et) * 2 + 0];
+            Q += s_fin[(gq * bn + et) * 2 + 1];
+          }
+          const double cnt = (double)a.M;
+          const double mean = Sm / cnt;
+          double var = Q / cnt - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const int c = n0 + et;
+          a.save_mean[c] = (float)mean;
+          a.save_invstd[c] = (float)(1.0 / sqrt(var + (double)a.eps));
+          const double unbiased = (a.M > 1) ? var * cnt / (cnt - 1.0) : var;
+          a.run_mean[c] = (1.f - a.momentum) * a.run_mean[c] + a.momentum * (float)mean;
+          a.run_var[c] = (1.f - a.momentum) * a.run_var[c] + a.momentum * (float)unbiased;
+        }
+      }
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  // a timed-out barrier (must never happen) poisons the output instead of hanging the GPU
+  if (s_fail && tid == 0) a.out[(size_t)n0] = __int_as_float(0x7fc00000);
+  if (warp == 4) umma::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int NT>
+size_t tcp_smem_bytes(int bn, int slices) {
+  const int b_slots = (slices == 1 && NT == 32) ? 9 : TP_BS;
+  return (size_t)TP_PS * 2 * TP_PATCH_BYTES + (size_t)b_slots * 2 * NT * 32 * sizeof(float) +
+         (size_t)128 * (bn + 1) * sizeof(float) + 1024;
+}
+
+template <int NT>
+int launch_tcp(const ConvArgs& a, cudaStream_t stream) {
+  const size_t smem = tcp_smem_bytes<NT>(a.tp_bn, a.tp_slices);
+  static size_t configured = 0;
+  if (smem > configured) {
+    B200OCL_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const TileGeom G = tile_geom(a.N, a.Hin, a.Win);
+  const int n_tiles = a.CN / a.tp_bn;
+  int gx = sm_count() / n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > G.tiles_m) gx = G.tiles_m;
+  // even out the tiles per CTA (e.g. 880 tiles on 148 CTAs = 6 rounds -> 147 CTAs of exactly 6)
+  const int rounds = (G.tiles_m + gx - 1) / gx;
+  gx = (G.tiles_m + rounds - 1) / rounds;
+  B200OCL_PROF(a.flip ? "conv_tc_dgrad" : (a.mode == CONV_EVAL ? "conv_tc_eval" : "conv_tc_train"),
+               2.0 * a.M * (double)a.CN * a.CK * 9.0, stream);
+  conv_tcp_kernel<NT><<<dim3(gx, n_tiles), TP_THREADS, smem, stream>>>(a);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
+
+}  // namespace
+
+bool conv_tcp_eligible(const ConvArgs& a) {
+  // read per call (a getenv is negligible next to a launch) so that tools can switch paths in-process
+  const char* e = getenv("B200OCL_TCP");
+  const char* e2 = getenv("B200OCL_TC");
+  const bool enabled = !((e && e[0] == '0') || (e2 && e2[0] == '0'));
+  if (!enabled || !a.w_tp || a.ks != 3 || a.stride != 1 || a.transposed || a.pad != 1) return false;
+  if (a.Hin != a.Hout || a.Win != a.Wout || a.CK % 4 != 0) return false;
+  if (a.Win % 8 != 0 || !(a.Hin % 16 == 0 || (a.Hin == 8 && a.Win == 8))) return false;
+  if (a.tp_bn <= 0 || a.tp_bn > 80 || a.CN % a.tp_bn != 0) return false;
+  // stat_part holds one row per persistent CTA; sized for conv_max_grid_m(M) >= tiles
+  return true;
+}
+
+int launch_conv_tcp(const ConvArgs& a, cudaStream_t stream) {
+  const int nt = a.tp_bn <= 20 ? 32 : (a.tp_bn <= 40 ? 48 : 80);
+  if (nt == 32) return launch_tcp<32>(a, stream);
+  if (nt == 48) return launch_tcp<48>(a, stream);
+  return launch_tcp<80>(a, stream);
+}
+
+}  // namespace b200ocl

@@ -700,6 +700,11 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
         a.tc_kb = c.tc_kb_d;
         a.tc_bn = c.tc_bn_d;
       }
+      if (c.tp_sl_d) {
+        a.w_tp = st->packed + c.tp_d_off;
+        a.tp_bn = c.tp_bn_d;
+        a.tp_slices = c.tp_sl_d;
+      }
     } else {
       a.transposed = 1;
       a.parity_order = (c.stride == 2 && c.hin % 2 == 0 && c.win % 2 == 0) ? 1 : 0;

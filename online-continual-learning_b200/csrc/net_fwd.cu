@@ -85,6 +85,54 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(TcPackTable t, const float
   }
 }
 
+// Halo-patch tensor-core images (conv_tcp.cu): blocks [channel tile][slice][tap][hi | lo][NT x 32], row n =
+// output channel of the direction, K slot = channel slice*32 + k of the contracted side, zero padded;
+// the data-gradient image stores tap t of the correlation = W[.][.][8 - t].
+struct TpPackTable {
+  int n;
+  struct {
+    unsigned int w_off, img_off;
+    int cin, cout, bn, nt, slices, dgrad;
+  } e[2 * NET_MAX_CONV];
+};
+
+__global__ void __launch_bounds__(256) tp_pack_kernel(TpPackTable t, const float* __restrict__ params,
+                                                      float* __restrict__ packed) {
+  const auto& L = t.e[blockIdx.y];
+  const int n_ch = L.dgrad ? L.cin : L.cout;
+  const int k_ch = L.dgrad ? L.cout : L.cin;
+  const int n_tiles = n_ch / L.bn;
+  const int total = n_tiles * L.slices * 9 * L.nt * 8;   // (tile, slice, tap, row, 16-byte chunk)
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int c = e & 7;
+    int r = e >> 3;
+    const int row = r % L.nt;
+    r /= L.nt;
+    const int tap = r % 9;
+    r /= 9;
+    const int sl = r % L.slices, tile = r / L.slices;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const int k0 = sl * 32 + c * 4;
+    if (row < L.bn && k0 < k_ch) {
+      const int nch = tile * L.bn + row;
+      const int wt = L.dgrad ? 8 - tap : tap;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int co = L.dgrad ? k0 + j : nch;
+        const int ci = L.dgrad ? nch : k0 + j;
+        v[j] = params[L.w_off + ((size_t)co * L.cin + ci) * 9 + wt];
+      }
+    }
+    float4 h, l;
+    umma::split_tf32(v[0], h.x, l.x); umma::split_tf32(v[1], h.y, l.y);
+    umma::split_tf32(v[2], h.z, l.z); umma::split_tf32(v[3], h.w, l.w);
+    float* base = packed + L.img_off + ((size_t)((tile * L.slices + sl) * 9 + tap) * 2) * L.nt * 32;
+    const int off = umma::sw128_offset_f32(row, c);
+    *reinterpret_cast<float4*>(base + off) = h;
+    *reinterpret_cast<float4*>(base + L.nt * 32 + off) = l;
+  }
+}
+
 int launch_pack(const NetPlan& p, const float* params, float* packed, cudaStream_t stream) {
   PackTable t{};
   t.n = p.n_conv;
@@ -117,6 +165,26 @@ int launch_pack(const NetPlan& p, const float* params, float* packed, cudaStream
   if (tc.n) {
     B200OCL_PROF("pack", 16.0 * p.n_packed / 2, stream);
     tc_pack_kernel<<<dim3(32, tc.n), 256, 0, stream>>>(tc, params, packed);
+    B200OCL_LAUNCHED();
+  }
+  TpPackTable tp{};
+  for (int i = 0; i < p.n_conv; ++i) {
+    const ConvL& c = p.conv[i];
+    if (!c.tp_sl_f) continue;
+    for (int d = 0; d < 2; ++d) {
+      auto& e = tp.e[tp.n++];
+      e.w_off = (unsigned)c.w_off;
+      e.img_off = (unsigned)(d ? c.tp_d_off : c.tp_f_off);
+      e.cin = c.cin; e.cout = c.cout;
+      e.bn = d ? c.tp_bn_d : c.tp_bn_f;
+      e.nt = tc_nt(e.bn);
+      e.slices = d ? c.tp_sl_d : c.tp_sl_f;
+      e.dgrad = d;
+    }
+  }
+  if (tp.n) {
+    B200OCL_PROF("pack", 16.0 * p.n_packed / 2, stream);
+    tp_pack_kernel<<<dim3(32, tp.n), 256, 0, stream>>>(tp, params, packed);
     B200OCL_LAUNCHED();
   }
   return B200OCL_OK;
@@ -342,6 +410,11 @@ void fill_conv_common(ConvArgs& a, const ConvL& c, int N, const float* in, const
     a.tc_kb = c.tc_kb_f;
     a.tc_bn = c.tc_bn_f;
   }
+  if (c.tp_sl_f) {
+    a.w_tp = packed + c.tp_f_off;
+    a.tp_bn = c.tp_bn_f;
+    a.tp_slices = c.tp_sl_f;
+  }
 }
 
 int conv_eval(const NetPlan& p, const b200ocl_net_state& st, int ci, int N, const float* in, float* out,
@@ -498,6 +571,84 @@ int b200ocl_net_pack(const b200ocl_net_desc* desc, const b200ocl_net_state* st, 
   int rc = check_state(desc, st, p);
   if (rc) return rc;
   return launch_pack(p, st->params, st->packed, static_cast<cudaStream_t>(stream));
+}
+
+static void selftest_layer(b200ocl::ConvL& c, int cin, int cout, int H, int W, size_t& pk) {
+  c = b200ocl::ConvL{};
+  c.cin = cin; c.cout = cout; c.ks = 3; c.stride = 1; c.pad = 1;
+  c.hin = c.hout = H; c.win = c.wout = W;
+  c.w_off = 0;
+  pk = 0;
+  b200ocl::conv_pack_layout(c, pk);
+}
+
+size_t b200ocl_conv_selftest_workspace_bytes(int N, int cin, int cout, int H, int W) {
+  b200ocl::ConvL c;
+  size_t pk = 0;
+  selftest_layer(c, cin, cout, H, W, pk);
+  const size_t M = (size_t)N * H * W;
+  const size_t stat = (size_t)b200ocl::conv_max_grid_m((int)M) * (cin > cout ? cin : cout) * 2 * sizeof(double);
+  return b200ocl::align_up(pk * sizeof(float), 256) + b200ocl::align_up(stat, 256) + 256 /* counters */ + 256;
+}
+
+int b200ocl_conv_selftest(const float* x, const float* w_oihw, float* out, int N, int H, int W, int cin, int cout,
+                          int dgrad, int path, int mode, float* stats_out, void* workspace, size_t workspace_bytes,
+                          void* stream_) {
+  using namespace b200ocl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200OCL_CHECK_ARG(x && w_oihw && out && workspace, "null pointer");
+  B200OCL_CHECK_ARG(N > 0 && H > 0 && W > 0 && cin % 20 == 0 && cout % 20 == 0 && cin > 0 && cout > 0, "bad shape");
+  B200OCL_CHECK_ARG(mode >= 0 && mode <= 2 && (mode != 2 || (stats_out && !dgrad)), "mode 2 (train) needs stats_out, forward only");
+  B200OCL_CHECK_ARG(workspace_bytes >= b200ocl_conv_selftest_workspace_bytes(N, cin, cout, H, W), "workspace too small");
+  NetPlan p;
+  memset(&p, 0, sizeof(p));
+  p.n_conv = 1;
+  size_t pk = 0;
+  selftest_layer(p.conv[0], cin, cout, H, W, pk);
+  p.n_packed = pk;
+  unsigned char* base = static_cast<unsigned char*>(workspace);
+  float* packed = reinterpret_cast<float*>(base);
+  double* stat_part = reinterpret_cast<double*>(base + align_up(pk * sizeof(float), 256));
+  const size_t M = (size_t)N * H * W;
+  const size_t stat = (size_t)conv_max_grid_m((int)M) * (cin > cout ? cin : cout) * 2 * sizeof(double);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(stat_part) + align_up(stat, 256));
+  int rc = launch_pack(p, w_oihw, packed, stream);
+  if (rc) return rc;
+  const ConvL& c = p.conv[0];
+  ConvArgs a{};
+  a.in = x;
+  a.out = out;
+  a.N = N;
+  a.Hin = a.Hout = H; a.Win = a.Wout = W;
+  a.ks = 3; a.stride = 1; a.pad = 1;
+  a.M = N * H * W;
+  a.mode = mode == 2 ? CONV_TRAIN : (mode == 1 ? CONV_ACCUM : CONV_RAW);
+  a.force_path = path;
+  a.eps = NET_BN_EPS;
+  a.momentum = NET_BN_MOMENTUM;
+  if (mode == 2) {
+    B200OCL_CUDA(cudaMemsetAsync(counters, 0, 64, stream));
+    B200OCL_CUDA(cudaMemsetAsync(stats_out, 0, (size_t)4 * cout * sizeof(float), stream));
+    a.stat_part = stat_part;
+    a.counter = counters;
+    a.save_mean = stats_out;
+    a.save_invstd = stats_out + cout;
+    a.run_mean = stats_out + 2 * cout;
+    a.run_var = stats_out + 3 * cout;
+  }
+  if (!dgrad) {
+    a.CK = cin; a.CN = cout;
+    a.w = packed + c.pkf_off;
+    if (c.tc_kb_f) { a.w_tc = packed + c.tc_f_off; a.tc_kb = c.tc_kb_f; a.tc_bn = c.tc_bn_f; }
+    if (c.tp_sl_f) { a.w_tp = packed + c.tp_f_off; a.tp_bn = c.tp_bn_f; a.tp_slices = c.tp_sl_f; }
+  } else {
+    a.CK = cout; a.CN = cin;
+    a.w = packed + c.pkd_off;
+    a.flip = 1;
+    if (c.tc_kb_d) { a.w_tc = packed + c.tc_d_off; a.tc_kb = c.tc_kb_d; a.tc_bn = c.tc_bn_d; }
+    if (c.tp_sl_d) { a.w_tp = packed + c.tp_d_off; a.tp_bn = c.tp_bn_d; a.tp_slices = c.tp_sl_d; }
+  }
+  return launch_conv(a, stream);
 }
 
 int b200ocl_net_sgd_step(const b200ocl_net_desc* desc, const b200ocl_net_state* st, float lr, float weight_decay,

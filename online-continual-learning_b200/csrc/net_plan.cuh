@@ -32,6 +32,11 @@ struct ConvL {
   size_t tc_f_off, tc_d_off;  // forward / flipped data-gradient image in the packed arena
   int tc_kb_f, tc_kb_d;       // K blocks: ceil(9*cin/32), ceil(9*cout/32)
   int tc_bn_f, tc_bn_d;       // real channels per tile: min(cout,80) / min(cin,80)
+  // halo-patch tensor-core kernel (conv_tcp.cu): [channel tile][32-channel slice][tap][hi | lo][NT x 32],
+  // taps of the data-gradient image already flipped; tp_sl_f == 0 when the geometry is not covered
+  size_t tp_f_off, tp_d_off;
+  int tp_sl_f, tp_sl_d;       // slices: ceil(cin/32), ceil(cout/32)
+  int tp_bn_f, tp_bn_d;       // real channels per tile: min(cout,40) / min(cin,40)
 };
 
 // padded MMA N for a channel tile of 20 / 40 / 80 channels (tcgen05 M=128 needs N % 16 == 0)
@@ -71,6 +76,30 @@ struct NetPlan {
 
 inline int conv_out(int x, int ks, int stride, int pad) { return (x + 2 * pad - ks) / stride + 1; }
 
+// Packed-arena layout of one convolution (kernel-side weight copies); c.cin/cout/ks/stride/hin/win set.
+inline void conv_pack_layout(ConvL& c, size_t& pk) {
+  const int cin = c.cin, cout = c.cout, ks = c.ks, stride = c.stride, hin = c.hin, win = c.win;
+  c.pkf_off = pk; pk += (size_t)cout * cin * ks * ks;
+  c.pkd_off = pk; pk += (size_t)cout * cin * ks * ks;
+  c.tc_kb_f = c.tc_kb_d = c.tp_sl_f = c.tp_sl_d = 0;
+  if (ks == 3 && stride == 1 && cin % 20 == 0) {
+    c.tc_bn_f = cout < 80 ? cout : 80;
+    c.tc_bn_d = cin < 80 ? cin : 80;
+    c.tc_kb_f = (9 * cin + 31) / 32;
+    c.tc_kb_d = (9 * cout + 31) / 32;
+    c.tc_f_off = pk; pk += (size_t)(cout / c.tc_bn_f) * c.tc_kb_f * 2 * tc_nt(c.tc_bn_f) * 32;
+    c.tc_d_off = pk; pk += (size_t)(cin / c.tc_bn_d) * c.tc_kb_d * 2 * tc_nt(c.tc_bn_d) * 32;
+  }
+  if (ks == 3 && stride == 1 && cin % 20 == 0 && win % 8 == 0 && (hin % 16 == 0 || (hin == 8 && win == 8))) {
+    c.tp_bn_f = cout < 40 ? cout : 40;
+    c.tp_bn_d = cin < 40 ? cin : 40;
+    c.tp_sl_f = (cin + 31) / 32;
+    c.tp_sl_d = (cout + 31) / 32;
+    c.tp_f_off = pk; pk += (size_t)(cout / c.tp_bn_f) * c.tp_sl_f * 9 * 2 * tc_nt(c.tp_bn_f) * 32;
+    c.tp_d_off = pk; pk += (size_t)(cin / c.tp_bn_d) * c.tp_sl_d * 9 * 2 * tc_nt(c.tp_bn_d) * 32;
+  }
+}
+
 // Returns 0 on success, a B200OCL_E* code otherwise.
 inline int build_plan(const b200ocl_net_desc& d, NetPlan& p) {
   memset(&p, 0, sizeof(p));
@@ -87,17 +116,8 @@ inline int build_plan(const b200ocl_net_desc& d, NetPlan& p) {
     c.hout = conv_out(hin, ks, stride, c.pad);
     c.wout = conv_out(win, ks, stride, c.pad);
     c.w_off = off; off += (size_t)cout * cin * ks * ks;
-    c.pkf_off = pk; pk += (size_t)cout * cin * ks * ks;
-    c.pkd_off = pk; pk += (size_t)cout * cin * ks * ks;
+    conv_pack_layout(c, pk);
     c.act_off = act;
-    if (ks == 3 && stride == 1 && cin % 20 == 0) {
-      c.tc_bn_f = cout < 80 ? cout : 80;
-      c.tc_bn_d = cin < 80 ? cin : 80;
-      c.tc_kb_f = (9 * cin + 31) / 32;
-      c.tc_kb_d = (9 * cout + 31) / 32;
-      c.tc_f_off = pk; pk += (size_t)(cout / c.tc_bn_f) * c.tc_kb_f * 2 * tc_nt(c.tc_bn_f) * 32;
-      c.tc_d_off = pk; pk += (size_t)(cin / c.tc_bn_d) * c.tc_kb_d * 2 * tc_nt(c.tc_bn_d) * 32;
-    }
     const size_t a = (size_t)c.hout * c.wout * cout;
     act += a;
     if (a > max_act) max_act = a;

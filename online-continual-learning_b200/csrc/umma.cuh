@@ -86,6 +86,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- one elected lane of a converged warp.  Unlike `lane == 0`, the elect.sync predicate keeps the region
+// warp-uniform for ptxas: tcgen05 / bulk-copy instructions inside are emitted once, without the per-active-lane
+// ELECT / BRA.U.ANY loops a divergent branch needs around every uniform-datapath instruction.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- MMA issue (one thread) and completion tracking
 __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
