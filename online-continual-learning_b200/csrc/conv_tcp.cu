@@ -19,10 +19,12 @@
 // hi*hi + hi*lo + lo*hi); each tap accumulates into its own TMEM buffer which the promotion warps
 // add into fp32 registers (a long TMEM accumulation truncates, see conv_tc.cu).  Roles:
 //   warps 0-3  promotion + epilogue (TMEM lane quarter = warp), folded eval BN / raw + batch statistics
-//   warp  4    MMA issue (one thread), TMEM allocation
-//   warp  5    weight loader (one thread): cp.async.bulk of pre-split, pre-swizzled [NT x 32] tiles,
+//   warps 4-6  MMA issue: K block q (tile, slice, tap) belongs to warp 4 + q % 3; one elected lane issues its
+//              MMAs and commits -- a single issuing warp is latency-bound at ~1 us per K block, three keep
+//              the tensor core fed; warp 4 also owns the TMEM allocation
+//   warp  7    weight loader (one elected lane): cp.async.bulk of pre-split, pre-swizzled [NT x 32] tiles,
 //              resident for the whole kernel when all 9 taps fit (cin <= 32), a 4-deep ring otherwise
-//   warps 6-9  patch loaders: coalesced LDG.128 of NHWC pixels, cvt.rna.tf32 split, swizzled stores
+//   warps 8-11 patch loaders: coalesced LDG.128 of NHWC pixels, cvt.rna.tf32 split, swizzled stores
 // CTAs are persistent over pixel tiles (one CTA per SM); batch statistics are accumulated per CTA in
 // fp64 in a fixed order and finalised by the last CTA (deterministic, as everywhere else).
 #include <stdlib.h>
@@ -33,7 +35,8 @@
 namespace b200ocl {
 namespace {
 
-constexpr int TP_THREADS = 320;
+constexpr int TP_MW = 3;                            // MMA-issuing warps (K block q is issued by warp q % TP_MW)
+constexpr int TP_THREADS = 32 * (4 + TP_MW + 1 + 4);
 constexpr int TP_PROWS = 200;                       // patch rows allocated per stage (180 or 200 used)
 constexpr int TP_PATCH_BYTES = TP_PROWS * 128;      // one of hi / lo
 constexpr int TP_PS = 2;                            // patch stages
@@ -53,15 +56,22 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
+// acc += the NT fp32 columns of this warp's 32 TMEM lanes: all loads issued, one wait
 template <int NT>
 __device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NT]) {
+  uint32_t r[NT];
 #pragma unroll
   for (int c0 = 0; c0 < NT; c0 += 16) {
-    float v[16];
-    umma::tmem_ld16(taddr + (uint32_t)c0, v);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[c0 + j] += v[j];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[c0 + 0]), "=r"(r[c0 + 1]), "=r"(r[c0 + 2]), "=r"(r[c0 + 3]), "=r"(r[c0 + 4]), "=r"(r[c0 + 5]),
+          "=r"(r[c0 + 6]), "=r"(r[c0 + 7]), "=r"(r[c0 + 8]), "=r"(r[c0 + 9]), "=r"(r[c0 + 10]), "=r"(r[c0 + 11]),
+          "=r"(r[c0 + 12]), "=r"(r[c0 + 13]), "=r"(r[c0 + 14]), "=r"(r[c0 + 15])
+        : "r"(taddr + (uint32_t)c0));
   }
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int c = 0; c < NT; ++c) acc[c] += __uint_as_float(r[c]);
 }
 
 struct TileGeom {
@@ -105,7 +115,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
   if (tid == 0) {
     for (int i = 0; i < TP_PS; ++i) {
       umma::mbar_init(&pfull[i], 128);
-      umma::mbar_init(&pempty[i], 1);
+      umma::mbar_init(&pempty[i], TP_MW);
     }
     for (int i = 0; i < 9; ++i) umma::mbar_init(&bfull[i], 1);
     for (int i = 0; i < TP_BS; ++i) umma::mbar_init(&bempty[i], 1);
@@ -122,9 +132,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
   const uint32_t tmem = tmem_slot;
   const float* wimg = a.w_tp + (size_t)blockIdx.y * slices * 9 * B_BLOCK;
 
-  if (warp >= 6) {
+  if (warp >= 5 + TP_MW) {
     // =========================================================== patch loaders (128 threads)
-    const int lt = tid - 192;
+    const int lt = tid - 32 * (5 + TP_MW);
     int pc = 0;
     for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
       const int tw = tile % G.tiles_w;
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
         umma::mbar_arrive(&pfull[ps]);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 4 + TP_MW) {
     // =========================================================== weight loader (one elected lane)
     const uint32_t bytes = (uint32_t)(B_BLOCK * sizeof(float));
     if (resident) {
@@ -200,8 +210,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
             __syncwarp();
           }
     }
-  } else if (warp == 4) {
-    // =========================================================== MMA issuer (whole warp waits, one elected lane issues)
+  } else if (warp >= 4) {
+    // =========================================================== MMA issuers (whole warp waits, one elected lane issues)
+    const int mw = warp - 4;                       // this warp issues the K blocks q with q % TP_MW == mw
     const uint32_t idesc = umma::make_idesc_tf32(128, NT);
     const uint64_t sbo_fix = ((uint64_t)((1280 >> 4) & 0x3FFF)) << 32;   // 8-row groups are 10 patch rows apart
     // descriptor templates: only the 14-bit start-address field (16-byte units) changes per stage / tap / K step
@@ -216,10 +227,18 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
       for (int sl = 0; sl < slices; ++sl, ++pc) {
         const int ps = pc % TP_PS;
         const int ksteps = (min(32, a.CK - sl * 32) + 7) / 8;
-        if (!umma::mbar_wait(&pfull[ps], (uint32_t)((pc / TP_PS) & 1))) s_fail = 1;
+        bool have_patch = false;
         const uint64_t dAs = dA0 + (uint64_t)(ps * A_STAGE);
+        int last_mine = -1;                         // this warp's last tap of the slice releases the patch stage
+        for (int tap = 8; tap >= 0; --tap)
+          if ((q + tap) % TP_MW == mw) { last_mine = tap; break; }
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap, ++q) {
+          if (q % TP_MW != mw) continue;
+          if (!have_patch) {
+            if (!umma::mbar_wait(&pfull[ps], (uint32_t)((pc / TP_PS) & 1))) s_fail = 1;
+            have_patch = true;
+          }
           const int b = resident ? tap : q % TP_BS;   // resident: slices == 1, block index = tap
           const int t = q % TP_NB;
           if (!umma::mbar_wait(&bfull[b], resident ? 0u : (uint32_t)((q / TP_BS) & 1))) s_fail = 1;
@@ -240,7 +259,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
             }
             if (!resident) umma::mma_commit(&bempty[b]);
             umma::mma_commit(&tfull[t]);
-            if (tap == 8) umma::mma_commit(&pempty[ps]);
+            if (tap == last_mine) umma::mma_commit(&pempty[ps]);
           }
           __syncwarp();
         }
@@ -405,7 +424,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
   __syncthreads();
   // a timed-out barrier (must never happen) poisons the output instead of hanging the GPU
   if (s_fail && tid == 0) a.out[(size_t)n0] = __int_as_float(0x7fc00000);
-  if (warp == 4) umma::tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == 4) umma::tmem_dealloc(tmem, TMEM_COLS);   // the allocating warp
 }
 
 template <int NT>
