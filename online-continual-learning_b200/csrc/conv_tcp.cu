@@ -35,13 +35,13 @@
 namespace b200ocl {
 namespace {
 
-constexpr int TP_MW = 3;                            // MMA-issuing warps (K block q is issued by warp q % TP_MW)
+constexpr int TP_MW = 3;                            // MMA-issuing warps: warp w issues the taps of kernel column kw = w
 constexpr int TP_THREADS = 32 * (4 + TP_MW + 1 + 4);
 constexpr int TP_PROWS = 200;                       // patch rows allocated per stage (180 or 200 used)
 constexpr int TP_PATCH_BYTES = TP_PROWS * 128;      // one of hi / lo
 constexpr int TP_PS = 2;                            // patch stages
-constexpr int TP_NB = 4;                            // TMEM accumulator buffers
-constexpr int TP_BS = 4;                            // weight ring depth (streaming mode)
+constexpr int TP_NB = 6;                            // TMEM accumulator buffers: two per MMA warp
+constexpr int TP_BS = 6;                            // weight ring depth (streaming mode): two blocks per MMA warp
 constexpr int TP_LD_MAX = 13;                       // 16-byte chunks a loader thread stages per patch (1600 / 128)
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -143,14 +143,16 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
       for (int sl = 0; sl < slices; ++sl, ++pc) {
         const int ch_valid = min(32, a.CK - sl * 32);       // real channels in this slice (multiple of 4)
         const int nch = 2 * ((ch_valid + 7) / 8);            // 16-byte chunks the MMAs will read per row
-        const int ntask = G.prow * 10 * nch;
+        // thread -> (patch row lt/8 + 16*i, chunk lt%8): no runtime divisions; lanes with chunk >= nch idle
+        const int ch = lt & 7, r0 = lt >> 3;
+        const int nrow = G.prow * 10;
+        const bool ch_live = ch < nch, ch_real = ch * 4 < ch_valid;
         float4 v[TP_LD_MAX];
 #pragma unroll
         for (int i = 0; i < TP_LD_MAX; ++i) {
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int task = lt + i * 128;
-          if (task < ntask) {
-            const int ri = task / nch, ch = task - ri * nch;
+          const int ri = r0 + 16 * i;
+          if (ch_real && ri < nrow) {
             const int P = ri / 10, c = ri - P * 10;
             int img, y;
             if (G.ipt == 2) {
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
               y = th * 16 + P - 1;
             }
             const int x = tw * 8 + c - 1;
-            if (img < a.N && (unsigned)y < (unsigned)a.Hin && (unsigned)x < (unsigned)a.Win && ch * 4 < ch_valid)
+            if (img < a.N && (unsigned)y < (unsigned)a.Hin && (unsigned)x < (unsigned)a.Win)
               v[i] = __ldg(reinterpret_cast<const float4*>(a.in + ((size_t)(img * a.Hin + y) * a.Win + x) * a.CK + sl * 32) + ch);
           }
         }
@@ -169,17 +171,18 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
         if (!umma::mbar_wait(&pempty[ps], (uint32_t)(((pc / TP_PS) & 1) ^ 1))) s_fail = 1;
         float* ph = reinterpret_cast<float*>(patch0 + (size_t)ps * 2 * TP_PATCH_BYTES);
         float* pl = ph + TP_PATCH_BYTES / 4;
+        if (ch_live) {
 #pragma unroll
-        for (int i = 0; i < TP_LD_MAX; ++i) {
-          const int task = lt + i * 128;
-          if (task < ntask) {
-            const int ri = task / nch, ch = task - ri * nch;
-            float4 h, l;
-            umma::split_tf32(v[i].x, h.x, l.x); umma::split_tf32(v[i].y, h.y, l.y);
-            umma::split_tf32(v[i].z, h.z, l.z); umma::split_tf32(v[i].w, h.w, l.w);
-            const int off = umma::sw128_offset_f32(ri, ch);
-            *reinterpret_cast<float4*>(ph + off) = h;
-            *reinterpret_cast<float4*>(pl + off) = l;
+          for (int i = 0; i < TP_LD_MAX; ++i) {
+            const int ri = r0 + 16 * i;
+            if (ri < nrow) {
+              float4 h, l;
+              umma::split_tf32(v[i].x, h.x, l.x); umma::split_tf32(v[i].y, h.y, l.y);
+              umma::split_tf32(v[i].z, h.z, l.z); umma::split_tf32(v[i].w, h.w, l.w);
+              const int off = umma::sw128_offset_f32(ri, ch);
+              *reinterpret_cast<float4*>(ph + off) = h;
+              *reinterpret_cast<float4*>(pl + off) = l;
+            }
           }
         }
         umma::fence_proxy_async_smem();
@@ -212,40 +215,39 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
     }
   } else if (warp >= 4) {
     // =========================================================== MMA issuers (whole warp waits, one elected lane issues)
-    const int mw = warp - 4;                       // this warp issues the K blocks q with q % TP_MW == mw
+    // Warp mw owns kernel column kw = mw (taps kh*3 + mw) and TMEM buffers 2*mw, 2*mw + 1, which it fills
+    // alternately; the promotion warps drain the taps in tap order, so the fp32 sum order is fixed.
+    const int mw = warp - 4;
     const uint32_t idesc = umma::make_idesc_tf32(128, NT);
     const uint64_t sbo_fix = ((uint64_t)((1280 >> 4) & 0x3FFF)) << 32;   // 8-row groups are 10 patch rows apart
     // descriptor templates: only the 14-bit start-address field (16-byte units) changes per stage / tap / K step
-    const uint64_t dA0 = (umma::make_smem_desc_sw128(umma::smem_u32(patch0)) & ~((uint64_t)0x3FFF << 32)) | sbo_fix;
+    const uint64_t dA0 = ((umma::make_smem_desc_sw128(umma::smem_u32(patch0)) & ~((uint64_t)0x3FFF << 32)) | sbo_fix) +
+                         (uint64_t)(mw * 8);                    // + kw patch rows of 128 bytes
     const uint64_t dB0 = umma::make_smem_desc_sw128(umma::smem_u32(sB));
     constexpr uint32_t A_LO = TP_PATCH_BYTES >> 4;           // hi -> lo patch, 16-byte units
     constexpr uint32_t A_STAGE = (2 * TP_PATCH_BYTES) >> 4;
     constexpr uint32_t B_LO = (NT * 128) >> 4;
     constexpr uint32_t B_SLOT = (B_BLOCK * 4) >> 4;
-    int q = 0, pc = 0;
+    const uint32_t a_kh = (uint32_t)(G.khs * 8);             // one kernel row further down the patch
+    int cnt = 0, pc = 0;                                      // K blocks issued by this warp; (tile, slice) pairs
+    bool b_ready = false;
     for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
       for (int sl = 0; sl < slices; ++sl, ++pc) {
         const int ps = pc % TP_PS;
         const int ksteps = (min(32, a.CK - sl * 32) + 7) / 8;
-        bool have_patch = false;
+        if (!umma::mbar_wait(&pfull[ps], (uint32_t)((pc / TP_PS) & 1))) s_fail = 1;
         const uint64_t dAs = dA0 + (uint64_t)(ps * A_STAGE);
-        int last_mine = -1;                         // this warp's last tap of the slice releases the patch stage
-        for (int tap = 8; tap >= 0; --tap)
-          if ((q + tap) % TP_MW == mw) { last_mine = tap; break; }
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap, ++q) {
-          if (q % TP_MW != mw) continue;
-          if (!have_patch) {
-            if (!umma::mbar_wait(&pfull[ps], (uint32_t)((pc / TP_PS) & 1))) s_fail = 1;
-            have_patch = true;
-          }
-          const int b = resident ? tap : q % TP_BS;   // resident: slices == 1, block index = tap
-          const int t = q % TP_NB;
-          if (!umma::mbar_wait(&bfull[b], resident ? 0u : (uint32_t)((q / TP_BS) & 1))) s_fail = 1;
-          if (!umma::mbar_wait(&tempty[t], (uint32_t)(((q / TP_NB) & 1) ^ 1))) s_fail = 1;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh, ++cnt) {
+          const int tap = kh * 3 + mw;
+          const int q = pc * 9 + tap;                  // position in the weight stream
+          const int b = resident ? tap : q % TP_BS;
+          const int t = 2 * mw + (cnt & 1);
+          if (!(resident && b_ready))
+            if (!umma::mbar_wait(&bfull[b], resident ? 0u : (uint32_t)((q / TP_BS) & 1))) s_fail = 1;
+          if (!umma::mbar_wait(&tempty[t], (uint32_t)(((cnt >> 1) & 1) ^ 1))) s_fail = 1;
           umma::fence_after_thread_sync();
-          const int kh = tap / 3, kw = tap - kh * 3;
-          const uint64_t dAh = dAs + (uint64_t)((kh * G.khs + kw) * 8);   // 128 bytes per patch row
+          const uint64_t dAh = dAs + (uint64_t)(kh * a_kh);
           const uint64_t dAl = dAh + A_LO;
           const uint64_t dBh = dB0 + (uint64_t)(b * B_SLOT);
           const uint64_t dBl = dBh + B_LO;
@@ -259,10 +261,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
             }
             if (!resident) umma::mma_commit(&bempty[b]);
             umma::mma_commit(&tfull[t]);
-            if (tap == last_mine) umma::mma_commit(&pempty[ps]);
+            if (kh == 2) umma::mma_commit(&pempty[ps]);
           }
           __syncwarp();
         }
+        b_ready = true;
       }
     }
   } else {
@@ -289,13 +292,18 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
       float acc[NT];
 #pragma unroll
       for (int c = 0; c < NT; ++c) acc[c] = 0.f;
-      for (int kb = 0; kb < slices * 9; ++kb, ++q) {
-        const int t = q % TP_NB;
-        if (!umma::mbar_wait(&tfull[t], (uint32_t)((q / TP_NB) & 1))) s_fail = 1;
-        umma::fence_after_thread_sync();
-        tmem_accumulate<NT>(my_lanes + (uint32_t)(t * NT), acc);
-        umma::fence_before_thread_sync();
-        umma::mbar_arrive(&tempty[t]);
+      for (int sl = 0; sl < slices; ++sl, ++q) {        // q counts (tile, slice) pairs here
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int kh = tap / 3, mwq = tap - 3 * kh;
+          const int cq = q * 3 + kh;                       // K blocks MMA warp mwq issued before this one
+          const int t = 2 * mwq + (cq & 1);
+          if (!umma::mbar_wait(&tfull[t], (uint32_t)((cq >> 1) & 1))) s_fail = 1;
+          umma::fence_after_thread_sync();
+          tmem_accumulate<NT>(my_lanes + (uint32_t)(t * NT), acc);
+          umma::fence_before_thread_sync();
+          umma::mbar_arrive(&tempty[t]);
+        }
       }
       int img, y;
       if (G.ipt == 2) {
@@ -467,16 +475,14 @@ bool conv_tcp_eligible(const ConvArgs& a) {
   if (!enabled || !a.w_tp || a.ks != 3 || a.stride != 1 || a.transposed || a.pad != 1) return false;
   if (a.Hin != a.Hout || a.Win != a.Wout || a.CK % 4 != 0) return false;
   if (a.Win % 8 != 0 || !(a.Hin % 16 == 0 || (a.Hin == 8 && a.Win == 8))) return false;
-  if (a.tp_bn <= 0 || a.tp_bn > 80 || a.CN % a.tp_bn != 0) return false;
+  if (a.tp_bn <= 0 || a.tp_bn > 40 || a.CN % a.tp_bn != 0) return false;
   // stat_part holds one row per persistent CTA; sized for conv_max_grid_m(M) >= tiles
   return true;
 }
 
 int launch_conv_tcp(const ConvArgs& a, cudaStream_t stream) {
-  const int nt = a.tp_bn <= 20 ? 32 : (a.tp_bn <= 40 ? 48 : 80);
-  if (nt == 32) return launch_tcp<32>(a, stream);
-  if (nt == 48) return launch_tcp<48>(a, stream);
-  return launch_tcp<80>(a, stream);
+  if (a.tp_bn <= 20) return launch_tcp<32>(a, stream);
+  return launch_tcp<48>(a, stream);   // tp_bn <= 40 (conv_tcp_eligible)
 }
 
 }  // namespace b200ocl

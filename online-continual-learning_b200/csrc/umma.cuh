@@ -68,6 +68,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // descriptor must not hang the GPU).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t max_spins = (1u << 24)) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1   // ptxas otherwise unrolls the poll 64x at every call site (160 KB of SASS in the conv kernels)
   for (uint32_t i = 0; i < max_spins; ++i) {
     uint32_t done;
     asm volatile(
