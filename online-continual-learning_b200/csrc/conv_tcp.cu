@@ -37,11 +37,9 @@ namespace {
 
 constexpr int TP_MW = 3;                            // MMA-issuing warps: warp w issues the taps of kernel column kw = w
 constexpr int TP_THREADS = 32 * (4 + TP_MW + 1 + 4);
-constexpr int TP_PROWS = 200;                       // patch rows allocated per stage (180 or 200 used)
-constexpr int TP_PATCH_BYTES = TP_PROWS * 128;      // one of hi / lo
-constexpr int TP_PS = 2;                            // patch stages
+constexpr int TP_PS_MAX = 3;                        // patch stages: 3 when shared memory allows, else 2
 constexpr int TP_NB = 6;                            // TMEM accumulator buffers: two per MMA warp
-constexpr int TP_BS = 6;                            // weight ring depth (streaming mode): two blocks per MMA warp
+constexpr int TP_BS_MAX = 6;                        // weight ring depth (streaming mode): 6 or 4
 constexpr int TP_LD_MAX = 13;                       // 16-byte chunks a loader thread stages per patch (1600 / 128)
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -77,6 +75,7 @@ __device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NT]
 struct TileGeom {
   int tiles_w, tiles_h, ipt, khs, prow;   // tiles per image row / column, images per tile, patch rows per kh, patch rows
   int tiles_m;
+  int pbytes;                             // bytes of one hi (or lo) patch, 1024-aligned
 };
 __host__ __device__ inline TileGeom tile_geom(int N, int H, int W) {
   TileGeom g;
@@ -86,17 +85,31 @@ __host__ __device__ inline TileGeom tile_geom(int N, int H, int W) {
   g.khs = 10 * g.ipt;
   g.prow = (g.ipt == 2) ? 20 : 18;
   g.tiles_m = ((N + g.ipt - 1) / g.ipt) * g.tiles_h * g.tiles_w;
+  g.pbytes = (g.prow * 10 * 128 + 1023) / 1024 * 1024;
   return g;
 }
 
-template <int NT>
+// KL: K steps (8 channels each) of the LAST 32-channel slice; every other slice has 4.  Compile-time so that the
+// issue sequence of a K block is straight-line code with immediate descriptor offsets (KL = 0: run-time loop).
+template <int KS>
+__device__ __forceinline__ void issue_kblock(uint32_t dcol, uint64_t dAh, uint64_t dAl, uint64_t dBh, uint64_t dBl,
+                                             uint32_t idesc) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const uint64_t adv = (uint64_t)(k * 2);   // 32 bytes per K step, in 16-byte units
+    umma::mma_tf32_ss(dcol, dAh + adv, dBh + adv, idesc, k > 0 ? 1u : 0u);
+    umma::mma_tf32_ss(dcol, dAh + adv, dBl + adv, idesc, 1u);
+    umma::mma_tf32_ss(dcol, dAl + adv, dBh + adv, idesc, 1u);
+  }
+}
+
+template <int NT, int KL>
 __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
   constexpr uint32_t TMEM_COLS = (TP_NB * NT <= 128) ? 128 : ((TP_NB * NT <= 256) ? 256 : 512);
   constexpr int B_BLOCK = 2 * NT * 32;   // floats: hi tile then lo tile
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* patch0 = smem_raw;                                          // [PS][hi | lo][PROWS][128 B]
-  float* sB = reinterpret_cast<float*>(smem_raw + TP_PS * 2 * TP_PATCH_BYTES);   // weight blocks
-  __shared__ __align__(8) uint64_t pfull[TP_PS], pempty[TP_PS], bfull[9], bempty[TP_BS], tfull[TP_NB], tempty[TP_NB];
+  __shared__ __align__(8) uint64_t pfull[TP_PS_MAX], pempty[TP_PS_MAX], bfull[9], bempty[TP_BS_MAX], tfull[TP_NB], tempty[TP_NB];
   __shared__ uint32_t tmem_slot;
   __shared__ bool is_last;
   __shared__ int s_fail;
@@ -107,18 +120,20 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
   const int n0 = blockIdx.y * bn;
   const int slices = a.tp_slices;
   const TileGeom G = tile_geom(a.N, a.Hin, a.Win);
+  const int PS = a.tp_ps, BS = a.tp_bs;            // patch stages, weight ring depth (launcher fits them to smem)
+  float* sB = reinterpret_cast<float*>(smem_raw + (size_t)PS * 2 * G.pbytes);   // weight blocks
   const bool resident = (slices == 1 && NT == 32);   // all 9 weight blocks stay in shared memory
-  const int b_slots = resident ? 9 : TP_BS;
+  const int b_slots = resident ? 9 : BS;
   float* s_t = sB + (size_t)b_slots * B_BLOCK;  // [128][bn + 1] transpose scratch for the batch statistics
 
   if (warp == 4) umma::tmem_alloc(&tmem_slot, TMEM_COLS);
   if (tid == 0) {
-    for (int i = 0; i < TP_PS; ++i) {
+    for (int i = 0; i < TP_PS_MAX; ++i) {
       umma::mbar_init(&pfull[i], 128);
       umma::mbar_init(&pempty[i], TP_MW);
     }
     for (int i = 0; i < 9; ++i) umma::mbar_init(&bfull[i], 1);
-    for (int i = 0; i < TP_BS; ++i) umma::mbar_init(&bempty[i], 1);
+    for (int i = 0; i < TP_BS_MAX; ++i) umma::mbar_init(&bempty[i], 1);
     for (int i = 0; i < TP_NB; ++i) {
       umma::mbar_init(&tfull[i], 1);
       umma::mbar_init(&tempty[i], 128);
@@ -167,10 +182,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
               v[i] = __ldg(reinterpret_cast<const float4*>(a.in + ((size_t)(img * a.Hin + y) * a.Win + x) * a.CK + sl * 32) + ch);
           }
         }
-        const int ps = pc % TP_PS;
-        if (!umma::mbar_wait(&pempty[ps], (uint32_t)(((pc / TP_PS) & 1) ^ 1))) s_fail = 1;
-        float* ph = reinterpret_cast<float*>(patch0 + (size_t)ps * 2 * TP_PATCH_BYTES);
-        float* pl = ph + TP_PATCH_BYTES / 4;
+        const int ps = pc % PS;
+        if (!umma::mbar_wait(&pempty[ps], (uint32_t)(((pc / PS) & 1) ^ 1))) s_fail = 1;
+        float* ph = reinterpret_cast<float*>(patch0 + (size_t)ps * 2 * G.pbytes);
+        float* pl = ph + G.pbytes / 4;
         if (ch_live) {
 #pragma unroll
           for (int i = 0; i < TP_LD_MAX; ++i) {
@@ -204,8 +219,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
       for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x)
         for (int sl = 0; sl < slices; ++sl)
           for (int tap = 0; tap < 9; ++tap, ++q) {
-            const int bs = q % TP_BS;
-            if (!umma::mbar_wait(&bempty[bs], (uint32_t)(((q / TP_BS) & 1) ^ 1))) s_fail = 1;
+            const int bs = q % BS;
+            if (!umma::mbar_wait(&bempty[bs], (uint32_t)(((q / BS) & 1) ^ 1))) s_fail = 1;
             if (umma::elect_one_sync()) {
               mbar_expect_tx(&bfull[bs], bytes);
               bulk_g2s(sB + (size_t)bs * B_BLOCK, wimg + (size_t)(sl * 9 + tap) * B_BLOCK, bytes, &bfull[bs]);
@@ -224,8 +239,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
     const uint64_t dA0 = ((umma::make_smem_desc_sw128(umma::smem_u32(patch0)) & ~((uint64_t)0x3FFF << 32)) | sbo_fix) +
                          (uint64_t)(mw * 8);                    // + kw patch rows of 128 bytes
     const uint64_t dB0 = umma::make_smem_desc_sw128(umma::smem_u32(sB));
-    constexpr uint32_t A_LO = TP_PATCH_BYTES >> 4;           // hi -> lo patch, 16-byte units
-    constexpr uint32_t A_STAGE = (2 * TP_PATCH_BYTES) >> 4;
+    const uint32_t A_LO = (uint32_t)G.pbytes >> 4;            // hi -> lo patch, 16-byte units
+    const uint32_t A_STAGE = (uint32_t)(2 * G.pbytes) >> 4;
     constexpr uint32_t B_LO = (NT * 128) >> 4;
     constexpr uint32_t B_SLOT = (B_BLOCK * 4) >> 4;
     const uint32_t a_kh = (uint32_t)(G.khs * 8);             // one kernel row further down the patch
@@ -233,18 +248,18 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
     bool b_ready = false;
     for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
       for (int sl = 0; sl < slices; ++sl, ++pc) {
-        const int ps = pc % TP_PS;
+        const int ps = pc % PS;
         const int ksteps = (min(32, a.CK - sl * 32) + 7) / 8;
-        if (!umma::mbar_wait(&pfull[ps], (uint32_t)((pc / TP_PS) & 1))) s_fail = 1;
+        if (!umma::mbar_wait(&pfull[ps], (uint32_t)((pc / PS) & 1))) s_fail = 1;
         const uint64_t dAs = dA0 + (uint64_t)(ps * A_STAGE);
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh, ++cnt) {
           const int tap = kh * 3 + mw;
           const int q = pc * 9 + tap;                  // position in the weight stream
-          const int b = resident ? tap : q % TP_BS;
+          const int b = resident ? tap : q % BS;
           const int t = 2 * mw + (cnt & 1);
           if (!(resident && b_ready))
-            if (!umma::mbar_wait(&bfull[b], resident ? 0u : (uint32_t)((q / TP_BS) & 1))) s_fail = 1;
+            if (!umma::mbar_wait(&bfull[b], resident ? 0u : (uint32_t)((q / BS) & 1))) s_fail = 1;
           if (!umma::mbar_wait(&tempty[t], (uint32_t)(((cnt >> 1) & 1) ^ 1))) s_fail = 1;
           umma::fence_after_thread_sync();
           const uint64_t dAh = dAs + (uint64_t)(kh * a_kh);
@@ -253,11 +268,17 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
           const uint64_t dBl = dBh + B_LO;
           const uint32_t dcol = tmem + (uint32_t)(t * NT);
           if (umma::elect_one_sync()) {
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adv = (uint64_t)(k * 2);   // 32 bytes per K step, in 16-byte units
-              umma::mma_tf32_ss(dcol, dAh + adv, dBh + adv, idesc, k > 0 ? 1u : 0u);
-              umma::mma_tf32_ss(dcol, dAh + adv, dBl + adv, idesc, 1u);
-              umma::mma_tf32_ss(dcol, dAl + adv, dBh + adv, idesc, 1u);
+            if (KL == 0) {
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t adv = (uint64_t)(k * 2);
+                umma::mma_tf32_ss(dcol, dAh + adv, dBh + adv, idesc, k > 0 ? 1u : 0u);
+                umma::mma_tf32_ss(dcol, dAh + adv, dBl + adv, idesc, 1u);
+                umma::mma_tf32_ss(dcol, dAl + adv, dBh + adv, idesc, 1u);
+              }
+            } else if (sl == slices - 1) {
+              issue_kblock<(KL > 0 ? KL : 1)>(dcol, dAh, dAl, dBh, dBl, idesc);
+            } else {
+              issue_kblock<4>(dcol, dAh, dAl, dBh, dBl, idesc);
             }
             if (!resident) umma::mma_commit(&bempty[b]);
             umma::mma_commit(&tfull[t]);
@@ -289,9 +310,39 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
       const int tw = tile % G.tiles_w;
       const int th = (tile / G.tiles_w) % G.tiles_h;
       const int ig = tile / (G.tiles_w * G.tiles_h);
-      float acc[NT];
+      int img, y;
+      if (G.ipt == 2) {
+        img = ig * 2 + (g & 1);
+        y = g >> 1;
+      } else {
+        img = ig;
+        y = th * 16 + g;
+      }
+      const int x = tw * 8 + r;
+      const bool valid = img < a.N;
+      const size_t m = ((size_t)img * a.Hout + y) * a.Wout + x;
+      // The accumulators start from what the epilogue would otherwise have to fetch after the last tap --
+      // the residual (eval) or the gradient being accumulated into (data gradient) -- so that global
+      // latency is paid while the tensor core works on the tile, not after it.
+      float acc[NT], pre[NT];
 #pragma unroll
-      for (int c = 0; c < NT; ++c) acc[c] = 0.f;
+      for (int c = 0; c < NT; ++c) {
+        acc[c] = 0.f;
+        pre[c] = 0.f;
+      }
+      {
+        const float* src = nullptr;
+        if (valid && a.mode == CONV_EVAL && a.residual) src = a.residual + m * a.CN + n0;
+        if (valid && a.mode == CONV_ACCUM) src = a.out + m * a.CN + n0;
+        if (src) {
+#pragma unroll
+          for (int c0 = 0; c0 < NT; c0 += 4) {
+            if (c0 >= bn) break;
+            const float4 v = *reinterpret_cast<const float4*>(src + c0);
+            pre[c0] = v.x; pre[c0 + 1] = v.y; pre[c0 + 2] = v.z; pre[c0 + 3] = v.w;
+          }
+        }
+      }
       for (int sl = 0; sl < slices; ++sl, ++q) {        // q counts (tile, slice) pairs here
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
@@ -305,35 +356,18 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
           umma::mbar_arrive(&tempty[t]);
         }
       }
-      int img, y;
-      if (G.ipt == 2) {
-        img = ig * 2 + (g & 1);
-        y = g >> 1;
-      } else {
-        img = ig;
-        y = th * 16 + g;
-      }
-      const int x = tw * 8 + r;
-      const bool valid = img < a.N;
-      const size_t m = ((size_t)img * a.Hout + y) * a.Wout + x;
       if (a.mode == CONV_EVAL) {
         if (valid) {
           float* o = a.out + m * a.CN + n0;
-          const float* rs = a.residual ? a.residual + m * a.CN + n0 : nullptr;
 #pragma unroll
           for (int c0 = 0; c0 < NT; c0 += 4) {
             if (c0 >= bn) break;
             float rr[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 4; ++j) {
               rr[j] = (acc[c0 + j] - s_coef[c0 + j]) * s_coef[80 + c0 + j] + s_coef[160 + c0 + j];
-            if (rs) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rs + c0);
-              rr[0] += r4.x; rr[1] += r4.y; rr[2] += r4.z; rr[3] += r4.w;
-            }
-            if (a.relu) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rr[j] = fmaxf(rr[j], 0.f);
+              rr[j] += pre[c0 + j];                       // residual (0 when there is none)
+              if (a.relu) rr[j] = fmaxf(rr[j], 0.f);
             }
             *reinterpret_cast<float4*>(o + c0) = make_float4(rr[0], rr[1], rr[2], rr[3]);
           }
@@ -344,30 +378,45 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
 #pragma unroll
           for (int c0 = 0; c0 < NT; c0 += 4) {
             if (c0 >= bn) break;
-            float4 rr = make_float4(acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]);
-            if (a.mode == CONV_ACCUM) {
-              const float4 old = *reinterpret_cast<const float4*>(o + c0);
-              rr.x += old.x; rr.y += old.y; rr.z += old.z; rr.w += old.w;
-            }
-            *reinterpret_cast<float4*>(o + c0) = rr;
+            // raw / train: pre == 0; accumulate: pre = previous contents
+            *reinterpret_cast<float4*>(o + c0) = make_float4(acc[c0] + pre[c0], acc[c0 + 1] + pre[c0 + 1],
+                                                             acc[c0 + 2] + pre[c0 + 2], acc[c0 + 3] + pre[c0 + 3]);
           }
         }
         if (a.mode == CONV_TRAIN) {
-          // transpose through shared memory; thread c sums its channel over the 128 rows in row order
-          // (rows of missing images hold exact zeros)
+          // transpose through shared memory; the 128 rows of a channel are summed in fp64 by 128 / bn threads
+          // (contiguous row ranges, combined in range order: the association is fixed)
 #pragma unroll
           for (int c = 0; c < NT; ++c)
             if (c < bn) s_t[et * (bn + 1) + c] = acc[c];
           esync();
-          if (et < bn) {
-            double S = 0.0, Q = 0.0;
-            for (int rr = 0; rr < 128; ++rr) {
-              const double xv = (double)s_t[rr * (bn + 1) + et];
+          const int parts = 128 / bn;                      // 6 (bn = 20) or 3 (bn = 40)
+          const int rows_pp = (128 + parts - 1) / parts;
+          const int ch = et % bn, part = et / bn;
+          double S = 0.0, Q = 0.0;
+          if (part < parts) {
+            const int r1 = min(128, (part + 1) * rows_pp);
+            for (int rr = part * rows_pp; rr < r1; ++rr) {
+              const double xv = (double)s_t[rr * (bn + 1) + ch];
               S += xv;
               Q += xv * xv;
             }
-            statS += S;
-            statQ += Q;
+          }
+          esync();                                         // s_t fully read
+          double* s_p = reinterpret_cast<double*>(s_t);    // [parts][bn][2] (<= 1920 B)
+          if (part < parts) {
+            s_p[(part * bn + ch) * 2 + 0] = S;
+            s_p[(part * bn + ch) * 2 + 1] = Q;
+          }
+          esync();
+          if (et < bn) {
+            double Ss = 0.0, Qs = 0.0;
+            for (int pp = 0; pp < parts; ++pp) {
+              Ss += s_p[(pp * bn + et) * 2 + 0];
+              Qs += s_p[(pp * bn + et) * 2 + 1];
+            }
+            statS += Ss;
+            statQ += Qs;
           }
           esync();
         }
@@ -436,18 +485,24 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
 }
 
 template <int NT>
-size_t tcp_smem_bytes(int bn, int slices) {
-  const int b_slots = (slices == 1 && NT == 32) ? 9 : TP_BS;
-  return (size_t)TP_PS * 2 * TP_PATCH_BYTES + (size_t)b_slots * 2 * NT * 32 * sizeof(float) +
+size_t tcp_smem_bytes(const TileGeom& G, int bn, int slices, int ps, int bs) {
+  const int b_slots = (slices == 1 && NT == 32) ? 9 : bs;
+  return (size_t)ps * 2 * G.pbytes + (size_t)b_slots * 2 * NT * 32 * sizeof(float) +
          (size_t)128 * (bn + 1) * sizeof(float) + 1024;
 }
 
-template <int NT>
-int launch_tcp(const ConvArgs& a, cudaStream_t stream) {
-  const size_t smem = tcp_smem_bytes<NT>(a.tp_bn, a.tp_slices);
+template <int NT, int KL>
+int launch_tcp(ConvArgs a, cudaStream_t stream) {
+  const TileGeom G0 = tile_geom(a.N, a.Hin, a.Win);
+  // deepest pipeline that fits: 3 patch stages + 6 weight slots, 3 + 4, else 2 + 6
+  const size_t limit = 227 * 1024 - 4096;     // static shared memory (barriers, coefficients) comes on top
+  a.tp_ps = 3; a.tp_bs = 6;
+  if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) a.tp_bs = 4;
+  if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) { a.tp_ps = 2; a.tp_bs = 6; }
+  const size_t smem = tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs);
   static size_t configured = 0;
   if (smem > configured) {
-    B200OCL_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200OCL_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<NT, KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const TileGeom G = tile_geom(a.N, a.Hin, a.Win);
@@ -460,7 +515,7 @@ int launch_tcp(const ConvArgs& a, cudaStream_t stream) {
   gx = (G.tiles_m + rounds - 1) / rounds;
   B200OCL_PROF(a.flip ? "conv_tc_dgrad" : (a.mode == CONV_EVAL ? "conv_tc_eval" : "conv_tc_train"),
                2.0 * a.M * (double)a.CN * a.CK * 9.0, stream);
-  conv_tcp_kernel<NT><<<dim3(gx, n_tiles), TP_THREADS, smem, stream>>>(a);
+  conv_tcp_kernel<NT, KL><<<dim3(gx, n_tiles), TP_THREADS, smem, stream>>>(a);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
 }
@@ -481,8 +536,16 @@ bool conv_tcp_eligible(const ConvArgs& a) {
 }
 
 int launch_conv_tcp(const ConvArgs& a, cudaStream_t stream) {
-  if (a.tp_bn <= 20) return launch_tcp<32>(a, stream);
-  return launch_tcp<48>(a, stream);   // tp_bn <= 40 (conv_tcp_eligible)
+  const int kl = (a.CK - 32 * (a.tp_slices - 1) + 7) / 8;   // K steps of the last slice
+  if (a.tp_bn <= 20) {
+    if (kl == 3 && a.tp_slices == 1) return launch_tcp<32, 3>(a, stream);   // 20 -> 20 channels
+    return launch_tcp<32, 0>(a, stream);
+  }
+  // tp_bn <= 40 (conv_tcp_eligible)
+  if (kl == 1) return launch_tcp<48, 1>(a, stream);   // 40 channels = 32 + 8
+  if (kl == 2) return launch_tcp<48, 2>(a, stream);   // 80 = 32 + 32 + 16
+  if (kl == 4) return launch_tcp<48, 4>(a, stream);   // 160
+  return launch_tcp<48, 0>(a, stream);
 }
 
 }  // namespace b200ocl
