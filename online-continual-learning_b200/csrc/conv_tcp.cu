@@ -6,14 +6,20 @@
 // arrays (TF32 hi / lo) of one 128-byte row per patch pixel, and the A operand of every tap is that
 // same array read through a shifted shared-memory descriptor:
 //
-//   tile   = 8 (w) x 16 (h) output pixels of one image   (or 8 x 8 of two images when H = 8)
-//   patch  = 18 x 10 pixels (20 x 10 with two interleaved images), row index P*10 + c, 128 B each
-//   MMA row 8g + r = output pixel (row g, column r)  ->  patch row (g + kh) * 10 + (r + kw)
-//          = descriptor start  base + (kh*10 + kw) * 128,  8-row groups 10 rows (1280 B) apart.
+//   strip  = the zero-padded input of the whole batch, row-major: position s = (img*(H+2) + yp)*(W+2) + xp,
+//            one 128-byte row (32 channel slots) per position, the halo positions hold zeros
+//   tile   = 128 consecutive strip positions = the 128 rows of an MMA; row i is the output pixel
+//            (img, y = yp, x = xp) when yp < H and xp < W, a discarded by-product otherwise
+//   tap (kh, kw) of row i reads strip position  s_i + kh*(W+2) + kw  -> one descriptor per tap whose start
+//            address is the patch base + (kh*(W+2) + kw) * 128 bytes; rows stay consecutive, so the 8-row
+//            groups are the standard 1024 bytes apart.
+// A stage therefore holds 128 + 2*(W+2) + 2 strip rows.  Any H, W works; the share of useful rows is
+// H*W / ((H+2)*(W+2)): 89 % at 32x32, 79 % at 16x16, 64 % at 8x8, 44 % at 4x4 -- tensor-core time is not
+// what bounds the kernel, and no im2col or per-shape tiling is needed.
 //
 // The hardware applies the 128-byte swizzle to absolute address bits, so a window that starts at any
 // 128-byte row of a patch stored with "chunk ^= row & 7" reads back exactly (tests/test_gpu_umma.py,
-// b200ocl_selftest_umma_window: every start row and an SBO of 10 rows, base-offset field 0).
+// b200ocl_selftest_umma_window: every start row, base-offset field 0).
 //
 // Per tile and slice the tensor core runs 9 taps x ceil(channels/8) K steps x 3 MMAs (3xTF32:
 // hi*hi + hi*lo + lo*hi); each tap accumulates into its own TMEM buffer which the promotion warps
@@ -40,7 +46,7 @@ constexpr int TP_THREADS = 32 * (4 + TP_MW + 1 + 4);
 constexpr int TP_PS_MAX = 3;                        // patch stages: 3 when shared memory allows, else 2
 constexpr int TP_NB = 6;                            // TMEM accumulator buffers: two per MMA warp
 constexpr int TP_BS_MAX = 6;                        // weight ring depth (streaming mode): 6 or 4
-constexpr int TP_LD_MAX = 13;                       // 16-byte chunks a loader thread stages per patch (1600 / 128)
+constexpr int TP_LD_MAX = 13;                       // patch rows a loader thread stages per tile (16 rows per pass)
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(umma::smem_u32(bar)), "r"(bytes)
@@ -73,19 +79,20 @@ __device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NT]
 }
 
 struct TileGeom {
-  int tiles_w, tiles_h, ipt, khs, prow;   // tiles per image row / column, images per tile, patch rows per kh, patch rows
-  int tiles_m;
-  int pbytes;                             // bytes of one hi (or lo) patch, 1024-aligned
+  int wp, pp;        // padded row length W + 2, padded image size (H + 2) * (W + 2)
+  int tiles_m;       // tiles of 128 strip positions
+  int prow;          // strip rows staged per tile: 128 + 2 * wp + 2
+  int pbytes;        // bytes of one hi (or lo) patch, 1024-aligned
 };
 __host__ __device__ inline TileGeom tile_geom(int N, int H, int W) {
   TileGeom g;
-  g.tiles_w = W / 8;
-  g.ipt = (H == 8) ? 2 : 1;
-  g.tiles_h = (g.ipt == 2) ? 1 : H / 16;
-  g.khs = 10 * g.ipt;
-  g.prow = (g.ipt == 2) ? 20 : 18;
-  g.tiles_m = ((N + g.ipt - 1) / g.ipt) * g.tiles_h * g.tiles_w;
-  g.pbytes = (g.prow * 10 * 128 + 1023) / 1024 * 1024;
+  g.wp = W + 2;
+  g.pp = (H + 2) * (W + 2);
+  // the last useful position is the last real pixel of the last image
+  const long last = (long)(N - 1) * g.pp + (long)(H - 1) * g.wp + (W - 1);
+  g.tiles_m = (int)(last / 128) + 1;
+  g.prow = 128 + 2 * g.wp + 2;
+  g.pbytes = (g.prow * 128 + 1023) / 1024 * 1024;
   return g;
 }
 
@@ -152,34 +159,40 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
     const int lt = tid - 32 * (5 + TP_MW);
     int pc = 0;
     for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
-      const int tw = tile % G.tiles_w;
-      const int th = (tile / G.tiles_w) % G.tiles_h;
-      const int ig = tile / (G.tiles_w * G.tiles_h);
       for (int sl = 0; sl < slices; ++sl, ++pc) {
         const int ch_valid = min(32, a.CK - sl * 32);       // real channels in this slice (multiple of 4)
         const int nch = 2 * ((ch_valid + 7) / 8);            // 16-byte chunks the MMAs will read per row
-        // thread -> (patch row lt/8 + 16*i, chunk lt%8): no runtime divisions; lanes with chunk >= nch idle
+        // thread -> (patch row lt/8 + 16*i, chunk lt%8): lanes with chunk >= nch idle
         const int ch = lt & 7, r0 = lt >> 3;
-        const int nrow = G.prow * 10;
+        const int nrow = G.prow;
         const bool ch_live = ch < nch, ch_real = ch * 4 < ch_valid;
         float4 v[TP_LD_MAX];
+        // strip position of this thread's first row, then 16 rows further per pass (no divisions in the loop)
+        int img, yp, xp;
+        {
+          const int sp = tile * 128 + r0;
+          img = sp / G.pp;
+          const int rem = sp - img * G.pp;
+          yp = rem / G.wp;
+          xp = rem - yp * G.wp;
+        }
+        const int hp = a.Hin + 2;
 #pragma unroll
         for (int i = 0; i < TP_LD_MAX; ++i) {
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int ri = r0 + 16 * i;
           if (ch_real && ri < nrow) {
-            const int P = ri / 10, c = ri - P * 10;
-            int img, y;
-            if (G.ipt == 2) {
-              img = ig * 2 + (P & 1);
-              y = (P >> 1) - 1;
-            } else {
-              img = ig;
-              y = th * 16 + P - 1;
-            }
-            const int x = tw * 8 + c - 1;
+            const int y = yp - 1, x = xp - 1;
             if (img < a.N && (unsigned)y < (unsigned)a.Hin && (unsigned)x < (unsigned)a.Win)
               v[i] = __ldg(reinterpret_cast<const float4*>(a.in + ((size_t)(img * a.Hin + y) * a.Win + x) * a.CK + sl * 32) + ch);
+          }
+          xp += 16;
+          while (xp >= G.wp) {
+            xp -= G.wp;
+            if (++yp == hp) {
+              yp = 0;
+              ++img;
+            }
           }
         }
         const int ps = pc % PS;
@@ -234,16 +247,14 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
     // alternately; the promotion warps drain the taps in tap order, so the fp32 sum order is fixed.
     const int mw = warp - 4;
     const uint32_t idesc = umma::make_idesc_tf32(128, NT);
-    const uint64_t sbo_fix = ((uint64_t)((1280 >> 4) & 0x3FFF)) << 32;   // 8-row groups are 10 patch rows apart
     // descriptor templates: only the 14-bit start-address field (16-byte units) changes per stage / tap / K step
-    const uint64_t dA0 = ((umma::make_smem_desc_sw128(umma::smem_u32(patch0)) & ~((uint64_t)0x3FFF << 32)) | sbo_fix) +
-                         (uint64_t)(mw * 8);                    // + kw patch rows of 128 bytes
+    const uint64_t dA0 = umma::make_smem_desc_sw128(umma::smem_u32(patch0)) + (uint64_t)(mw * 8);   // + kw rows of 128 B
     const uint64_t dB0 = umma::make_smem_desc_sw128(umma::smem_u32(sB));
     const uint32_t A_LO = (uint32_t)G.pbytes >> 4;            // hi -> lo patch, 16-byte units
     const uint32_t A_STAGE = (uint32_t)(2 * G.pbytes) >> 4;
     constexpr uint32_t B_LO = (NT * 128) >> 4;
     constexpr uint32_t B_SLOT = (B_BLOCK * 4) >> 4;
-    const uint32_t a_kh = (uint32_t)(G.khs * 8);             // one kernel row further down the patch
+    const uint32_t a_kh = (uint32_t)(G.wp * 8);              // one kernel row = W + 2 strip rows further
     int cnt = 0, pc = 0;                                      // K blocks issued by this warp; (tile, slice) pairs
     bool b_ready = false;
     for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
@@ -303,23 +314,13 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
       }
       esync();
     }
-    const int g = et >> 3, r = et & 7;
     double statS = 0.0, statQ = 0.0;           // thread c < bn: running sums of channel c over this CTA's tiles
     int q = 0;
     for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
-      const int tw = tile % G.tiles_w;
-      const int th = (tile / G.tiles_w) % G.tiles_h;
-      const int ig = tile / (G.tiles_w * G.tiles_h);
-      int img, y;
-      if (G.ipt == 2) {
-        img = ig * 2 + (g & 1);
-        y = g >> 1;
-      } else {
-        img = ig;
-        y = th * 16 + g;
-      }
-      const int x = tw * 8 + r;
-      const bool valid = img < a.N;
+      const int sp = tile * 128 + et;                    // strip position of this MMA row
+      const int img = sp / G.pp, rem = sp - img * G.pp;
+      const int y = rem / G.wp, x = rem - y * G.wp;
+      const bool valid = img < a.N && y < a.Hout && x < a.Wout;   // halo positions are by-products
       const size_t m = ((size_t)img * a.Hout + y) * a.Wout + x;
       // The accumulators start from what the epilogue would otherwise have to fetch after the last tap --
       // the residual (eval) or the gradient being accumulated into (data gradient) -- so that global
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
           // (contiguous row ranges, combined in range order: the association is fixed)
 #pragma unroll
           for (int c = 0; c < NT; ++c)
-            if (c < bn) s_t[et * (bn + 1) + c] = acc[c];
+            if (c < bn) s_t[et * (bn + 1) + c] = valid ? acc[c] : 0.f;   // by-product rows do not count
           esync();
           const int parts = 128 / bn;                      // 6 (bn = 20) or 3 (bn = 40)
           const int rows_pp = (128 + parts - 1) / parts;
@@ -529,7 +530,8 @@ bool conv_tcp_eligible(const ConvArgs& a) {
   const bool enabled = !((e && e[0] == '0') || (e2 && e2[0] == '0'));
   if (!enabled || !a.w_tp || a.ks != 3 || a.stride != 1 || a.transposed || a.pad != 1) return false;
   if (a.Hin != a.Hout || a.Win != a.Wout || a.CK % 4 != 0) return false;
-  if (a.Win % 8 != 0 || !(a.Hin % 16 == 0 || (a.Hin == 8 && a.Win == 8))) return false;
+  if (128 + 2 * (a.Win + 2) + 2 > 16 * TP_LD_MAX) return false;   // strip rows one stage holds (W <= 37)
+  if ((long)a.N * (a.Hin + 2) * (a.Win + 2) > 2000000000L) return false;
   if (a.tp_bn <= 0 || a.tp_bn > 40 || a.CN % a.tp_bn != 0) return false;
   // stat_part holds one row per persistent CTA; sized for conv_max_grid_m(M) >= tiles
   return true;

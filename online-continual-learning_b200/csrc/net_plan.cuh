@@ -90,7 +90,7 @@ inline void conv_pack_layout(ConvL& c, size_t& pk) {
     c.tc_f_off = pk; pk += (size_t)(cout / c.tc_bn_f) * c.tc_kb_f * 2 * tc_nt(c.tc_bn_f) * 32;
     c.tc_d_off = pk; pk += (size_t)(cin / c.tc_bn_d) * c.tc_kb_d * 2 * tc_nt(c.tc_bn_d) * 32;
   }
-  if (ks == 3 && stride == 1 && cin % 20 == 0 && win % 8 == 0 && (hin % 16 == 0 || (hin == 8 && win == 8))) {
+  if (ks == 3 && stride == 1 && cin % 20 == 0 && win <= 37) {   // conv_tcp.cu: one stage holds 128 + 2*(W+2) + 2 strip rows
     c.tp_bn_f = cout < 40 ? cout : 40;
     c.tp_bn_d = cin < 40 ? cin : 40;
     c.tp_sl_f = (cin + 31) / 32;

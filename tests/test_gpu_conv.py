@@ -42,6 +42,7 @@ SHAPES = [  # N, H, W, cin, cout
     (10, 32, 32, 20, 20), (110, 32, 32, 20, 20), (7, 16, 16, 40, 40), (110, 16, 16, 40, 40),
     (10, 8, 8, 80, 80), (7, 8, 8, 80, 80), (110, 8, 8, 80, 80), (3, 16, 16, 20, 40), (5, 8, 8, 40, 80),
     (1, 8, 8, 80, 80), (2, 32, 32, 20, 20), (64, 16, 16, 160, 160), (8, 8, 8, 80, 80), (8, 16, 16, 40, 40), (8, 32, 32, 20, 20),
+    (10, 4, 4, 160, 160), (110, 4, 4, 160, 160), (7, 4, 4, 160, 160), (5, 21, 21, 40, 40), (3, 11, 11, 80, 80), (2, 6, 6, 160, 160),
 ]
 
 
