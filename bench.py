@@ -181,7 +181,8 @@ def run_ours(args, rank, world):
         for i in range(args.warmup):
             step(i, from_host)
         barrier()
-        launches0 = _native.launch_count()
+        from b200ocl import engine as _eng
+        launches0 = _native.launch_count() + _eng.graph_launch_count()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
@@ -199,7 +200,7 @@ def run_ours(args, rank, world):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), _native.launch_count() - launches0, clocks, wall
+        return float(t.item()), _native.launch_count() + _eng.graph_launch_count() - launches0, clocks, wall
 
     log('rank %d: learners built' % rank)
     ms_dev, launches, clocks, wall = timed(False)
@@ -210,7 +211,11 @@ def run_ours(args, rank, world):
         return None
     imgs = 2 * BATCH * world * args.steps
     # per-kernel-class device time of one step (separate pass, event-bracketed inside the library)
+    from b200ocl import engine as _engine
+    _graphs_were = _engine._GRAPHS
+    _engine.set_graphs(False)                 # the per-launch profiler needs eager launches (same kernels)
     prof = profile_step(lambda i: step(i, False), args.warmup + args.steps - 1) if world == 1 else None
+    _engine.set_graphs(_graphs_were)
     pk = peaks()
     line = {
         'metric': 'replay-step images/sec (ASER+SCR, ResNet18, CIFAR100)', 'value': imgs / (ms_dev * 1e-3),

@@ -64,6 +64,54 @@ class ArenaState:
                           self.packed.data_ptr(), self.bn_stats.data_ptr(), self.bn_tracked.data_ptr())
 
 
+# CUDA graphs for the network-level calls (40-120 kernel launches each): after two eager calls of a given
+# (call, batch size, workspace) the launch sequence is captured once and replayed.  Replays read their inputs from
+# static buffers (one device-to-device copy per call).  B200OCL_GRAPHS=0 or set_graphs(False) turns this off
+# (the per-launch profiler needs eager launches).
+import os as _os
+_GRAPHS = _os.environ.get('B200OCL_GRAPHS', '1') != '0'
+
+
+def set_graphs(on):
+    global _GRAPHS
+    _GRAPHS = bool(on)
+
+
+_replayed = [0]      # kernel launches issued through graph replays (the library's own counter only sees eager ones)
+
+
+def graph_launch_count():
+    return _replayed[0]
+
+
+class _Graphed:
+    """One captured call: static inputs / outputs, the graphs, and the number of eager warm-up calls so far.
+    The same launch sequence is captured into N_EXEC executable graphs used round-robin, so that a replay never
+    has to wait for the previous launch of the same executable when the host runs several steps ahead."""
+    __slots__ = ('inputs', 'outputs', 'graphs', 'calls', 'kernels', 'turn')
+    N_EXEC = 3
+
+    def __init__(self, inputs, outputs):
+        self.inputs, self.outputs, self.graphs, self.calls, self.kernels, self.turn = inputs, outputs, [], 0, 0, 0
+
+    def run(self, launch):
+        if self.calls < 1:                       # eager once: lets every launcher configure its kernel
+            launch()
+            self.calls += 1
+            return
+        if not self.graphs:                      # second call: capture all executables, run the first
+            for _ in range(self.N_EXEC):
+                before = _native.launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    launch()
+                self.kernels = int(_native.launch_count() - before)
+                self.graphs.append(g)
+        self.graphs[self.turn].replay()
+        self.turn = (self.turn + 1) % self.N_EXEC
+        _replayed[0] += self.kernels
+
+
 class Engine:
     def __init__(self, in_hw, num_classes, head=None, feat_dim=128, device='cuda'):
         self.desc, self.info, self.table = describe(in_hw, num_classes, head, feat_dim)
@@ -77,6 +125,7 @@ class Engine:
         self._virtual = None
         self._eval_ws = {}
         self._train_ws = {}
+        self._graphs = {}
 
     # ------------------------------------------------------------------ state
     def param_views(self, shapes=None):
@@ -141,9 +190,8 @@ class Engine:
         """model.eval(); model.features(x) under no_grad -> [N, dim_in]."""
         x = self._x(x)
         n = x.shape[0]
-        feat = torch.empty((n, self.dim_in), dtype=torch.float32, device=x.device)
         if n == 0:
-            return feat
+            return torch.empty((0, self.dim_in), dtype=torch.float32, device=x.device)
         lib = _lib()
         ws = self._eval_ws.get(n)
         if ws is None:
@@ -151,9 +199,23 @@ class Engine:
             if len(self._eval_ws) < 8:
                 self._eval_ws[n] = ws
         st = state or self.state
-        rc = lib.b200ocl_net_features_eval(ctypes.byref(self.desc), ctypes.byref(st.c), x.data_ptr(), n,
-                                           feat.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
-        _native.check(rc, 'b200ocl_net_features_eval')
+
+        def launch(xin, feat):
+            rc = lib.b200ocl_net_features_eval(ctypes.byref(self.desc), ctypes.byref(st.c), xin.data_ptr(), n,
+                                               feat.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+            _native.check(rc, 'b200ocl_net_features_eval')
+
+        if _GRAPHS and state is None and self._eval_ws.get(n) is ws:
+            key = ('eval', n)
+            e = self._graphs.get(key)
+            if e is None:
+                e = self._graphs[key] = _Graphed([torch.empty_like(x)],
+                                                 [torch.empty((n, self.dim_in), dtype=torch.float32, device=x.device)])
+            e.inputs[0].copy_(x)
+            e.run(lambda: launch(e.inputs[0], e.outputs[0]))
+            return e.outputs[0].clone()          # the static buffer is overwritten by the next call
+        feat = torch.empty((n, self.dim_in), dtype=torch.float32, device=x.device)
+        launch(x, feat)
         return feat
 
     def new_train_workspace(self, n):
@@ -169,16 +231,31 @@ class Engine:
         return ws
 
     def forward_train(self, x, ws=None, state=None, slot=0):
-        """model.train(); model.forward(x).  Returns (out [N,out_dim], workspace kept for backward)."""
+        """model.train(); model.forward(x).  Returns (out [N,out_dim], workspace kept for backward).
+        """
         x = self._x(x)
         n = x.shape[0]
+        graphed = _GRAPHS and ws is None and state is None and (n, slot) in self._train_ws
         if ws is None:
             ws = self.train_workspace(n, slot)
-        out = torch.empty((n, self.out_dim), dtype=torch.float32, device=x.device)
         st = state or self.state
-        rc = _lib().b200ocl_net_forward_train(ctypes.byref(self.desc), ctypes.byref(st.c), x.data_ptr(), n,
-                                              out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
-        _native.check(rc, 'b200ocl_net_forward_train')
+
+        def launch(xin, out):
+            rc = _lib().b200ocl_net_forward_train(ctypes.byref(self.desc), ctypes.byref(st.c), xin.data_ptr(), n,
+                                                  out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+            _native.check(rc, 'b200ocl_net_forward_train')
+
+        if graphed:
+            key = ('fwd', n, slot)
+            e = self._graphs.get(key)
+            if e is None:
+                e = self._graphs[key] = _Graphed([torch.empty_like(x)],
+                                                 [torch.empty((n, self.out_dim), dtype=torch.float32, device=x.device)])
+            e.inputs[0].copy_(x)
+            e.run(lambda: launch(e.inputs[0], e.outputs[0]))
+            return e.outputs[0].clone(), ws      # the static buffer is overwritten by the next call
+        out = torch.empty((n, self.out_dim), dtype=torch.float32, device=x.device)
+        launch(x, out)
         return out, ws
 
     def backward(self, x, dout, ws, accumulate=False):
@@ -189,10 +266,25 @@ class Engine:
         n = dout.shape[0]
         if x.shape[0] != n or dout.shape[1] != self.out_dim:
             raise ValueError('dout must be [N, out_dim] for the same N as x')
-        rc = _lib().b200ocl_net_backward(ctypes.byref(self.desc), ctypes.byref(self.state.c), x.data_ptr(),
-                                         dout.data_ptr(), n, ws.data_ptr(), ws.numel(), 1 if accumulate else 0,
-                                         _stream())
-        _native.check(rc, 'b200ocl_net_backward')
+
+        def launch(xin, din):
+            rc = _lib().b200ocl_net_backward(ctypes.byref(self.desc), ctypes.byref(self.state.c), xin.data_ptr(),
+                                             din.data_ptr(), n, ws.data_ptr(), ws.numel(), 1 if accumulate else 0,
+                                             _stream())
+            _native.check(rc, 'b200ocl_net_backward')
+
+        slot = next((k[1] for k, w in self._train_ws.items() if w is ws and k[0] == n), None) if _GRAPHS else None
+        fwd = self._graphs.get(('fwd', n, slot)) if slot is not None else None
+        if fwd is not None:
+            # the images are the static copy the graphed forward read (same data as x)
+            key = ('bwd', n, slot, bool(accumulate))
+            e = self._graphs.get(key)
+            if e is None:
+                e = self._graphs[key] = _Graphed([fwd.inputs[0], torch.empty_like(dout)], [])
+            e.inputs[1].copy_(dout)
+            e.run(lambda: launch(e.inputs[0], e.inputs[1]))
+            return
+        launch(x, dout)
 
     def sgd_step(self, lr, weight_decay=0.0, dst=None):
         rc = _lib().b200ocl_net_sgd_step(ctypes.byref(self.desc), ctypes.byref(self.state.c), float(lr),

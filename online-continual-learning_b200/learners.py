@@ -97,6 +97,18 @@ class ContinualLearner(torch.nn.Module):
         self.grad_sync = None      # data-parallel stream shards: callable(engine) summing gradients over ranks
         self.grad_world = 1
 
+    def _throttle(self, depth=2):
+        """Keep the host at most `depth` replay steps ahead of the GPU: the stream never runs dry, the launch
+        queue stays short, and a CUDA-graph executable is never relaunched while it is still running."""
+        if not torch.cuda.is_available():
+            return
+        ring = self.__dict__.setdefault('_step_events', [])
+        ev = torch.cuda.Event()
+        ev.record()
+        ring.append(ev)
+        if len(ring) > depth:
+            ring.pop(0).synchronize()
+
     def _lr_wd(self):
         """Step size / weight decay from the optimizer the caller built (run.py:40).  Only plain
         SGD is implemented (setup_elements.py:73-75, the reference default)."""
@@ -232,6 +244,7 @@ class ExperienceReplay(ContinualLearner):
                 self.last_loss = ce['loss']
             self._optimizer_step(lr, wd)                                            # :87 / :89
         self.buffer.update(batch_x, batch_y, y_host=batch_y_host)                   # :92
+        self._throttle()
 
     def train_learner(self, x_train, y_train):
         self.before_train(x_train, y_train)
@@ -280,6 +293,7 @@ class SupContrastReplay(ContinualLearner):
                 if meters is not None:
                     meters['losses'].update(loss, batch_y.size(0))
         self.buffer.update(batch_x, batch_y, y_host=batch_y_host)                   # :63
+        self._throttle()
 
     def train_learner(self, x_train, y_train):
         self.before_train(x_train, y_train)
