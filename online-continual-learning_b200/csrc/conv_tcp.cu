@@ -100,11 +100,11 @@ __host__ __device__ inline TileGeom tile_geom(int N, int H, int W) {
 // issue sequence of a K block is straight-line code with immediate descriptor offsets (KL = 0: run-time loop).
 template <int KS>
 __device__ __forceinline__ void issue_kblock(uint32_t dcol, uint64_t dAh, uint64_t dAl, uint64_t dBh, uint64_t dBl,
-                                             uint32_t idesc) {
+                                             uint32_t idesc, uint32_t acc0) {
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
     const uint64_t adv = (uint64_t)(k * 2);   // 32 bytes per K step, in 16-byte units
-    umma::mma_tf32_ss(dcol, dAh + adv, dBh + adv, idesc, k > 0 ? 1u : 0u);
+    umma::mma_tf32_ss(dcol, dAh + adv, dBh + adv, idesc, k > 0 ? 1u : acc0);
     umma::mma_tf32_ss(dcol, dAh + adv, dBl + adv, idesc, 1u);
     umma::mma_tf32_ss(dcol, dAl + adv, dBh + adv, idesc, 1u);
   }
@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
   const int slices = a.tp_slices;
   const TileGeom G = tile_geom(a.N, a.Hin, a.Win);
   const int PS = a.tp_ps, BS = a.tp_bs;            // patch stages, weight ring depth (launcher fits them to smem)
+  const bool chain3 = a.tp_chain == 3;
   float* sB = reinterpret_cast<float*>(smem_raw + (size_t)PS * 2 * G.pbytes);   // weight blocks
   const bool resident = (slices == 1 && NT == 32);   // all 9 weight blocks stay in shared memory
   const int b_slots = resident ? 9 : BS;
@@ -268,31 +269,36 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
           const int tap = kh * 3 + mw;
           const int q = pc * 9 + tap;                  // position in the weight stream
           const int b = resident ? tap : q % BS;
-          const int t = 2 * mw + (cnt & 1);
+          // chain == 1: every tap has its own TMEM buffer and is promoted separately; chain == 3: the three
+          // taps of this warp's kernel column accumulate in one buffer (a TMEM chain of <= 96 products)
+          const int cb = chain3 ? pc : cnt;
+          const int t = 2 * mw + (cb & 1);
           if (!(resident && b_ready))
             if (!umma::mbar_wait(&bfull[b], resident ? 0u : (uint32_t)((q / BS) & 1))) s_fail = 1;
-          if (!umma::mbar_wait(&tempty[t], (uint32_t)(((cnt >> 1) & 1) ^ 1))) s_fail = 1;
+          if (!chain3 || kh == 0)
+            if (!umma::mbar_wait(&tempty[t], (uint32_t)(((cb >> 1) & 1) ^ 1))) s_fail = 1;
           umma::fence_after_thread_sync();
           const uint64_t dAh = dAs + (uint64_t)(kh * a_kh);
           const uint64_t dAl = dAh + A_LO;
           const uint64_t dBh = dB0 + (uint64_t)(b * B_SLOT);
           const uint64_t dBl = dBh + B_LO;
           const uint32_t dcol = tmem + (uint32_t)(t * NT);
+          const uint32_t acc0 = (chain3 && kh > 0) ? 1u : 0u;
           if (umma::elect_one_sync()) {
             if (KL == 0) {
               for (int k = 0; k < ksteps; ++k) {
                 const uint64_t adv = (uint64_t)(k * 2);
-                umma::mma_tf32_ss(dcol, dAh + adv, dBh + adv, idesc, k > 0 ? 1u : 0u);
+                umma::mma_tf32_ss(dcol, dAh + adv, dBh + adv, idesc, k > 0 ? 1u : acc0);
                 umma::mma_tf32_ss(dcol, dAh + adv, dBl + adv, idesc, 1u);
                 umma::mma_tf32_ss(dcol, dAl + adv, dBh + adv, idesc, 1u);
               }
             } else if (sl == slices - 1) {
-              issue_kblock<(KL > 0 ? KL : 1)>(dcol, dAh, dAl, dBh, dBl, idesc);
+              issue_kblock<(KL > 0 ? KL : 1)>(dcol, dAh, dAl, dBh, dBl, idesc, acc0);
             } else {
-              issue_kblock<4>(dcol, dAh, dAl, dBh, dBl, idesc);
+              issue_kblock<4>(dcol, dAh, dAl, dBh, dBl, idesc, acc0);
             }
             if (!resident) umma::mma_commit(&bempty[b]);
-            umma::mma_commit(&tfull[t]);
+            if (!chain3 || kh == 2) umma::mma_commit(&tfull[t]);
             if (kh == 2) umma::mma_commit(&pempty[ps]);
           }
           __syncwarp();
@@ -346,9 +352,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
       }
       for (int sl = 0; sl < slices; ++sl, ++q) {        // q counts (tile, slice) pairs here
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const int kh = tap / 3, mwq = tap - 3 * kh;
-          const int cq = q * 3 + kh;                       // K blocks MMA warp mwq issued before this one
+        for (int tap = 0; tap < (chain3 ? 3 : 9); ++tap) {
+          const int kh = chain3 ? 0 : tap / 3, mwq = tap - 3 * kh;
+          const int cq = chain3 ? q : q * 3 + kh;          // buffers MMA warp mwq filled before this one
           const int t = 2 * mwq + (cq & 1);
           if (!umma::mbar_wait(&tfull[t], (uint32_t)((cq >> 1) & 1))) s_fail = 1;
           umma::fence_after_thread_sync();
@@ -498,6 +504,10 @@ int launch_tcp(ConvArgs a, cudaStream_t stream) {
   // deepest pipeline that fits: 3 patch stages + 6 weight slots, 3 + 4, else 2 + 6
   const size_t limit = 227 * 1024 - 4096;     // static shared memory (barriers, coefficients) comes on top
   a.tp_ps = 3; a.tp_bs = 6;
+  {
+    const char* e = getenv("B200OCL_TCP_CHAIN");
+    a.tp_chain = (e && e[0] == '3') ? 3 : 1;
+  }
   if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) a.tp_bs = 4;
   if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) { a.tp_ps = 2; a.tp_bs = 6; }
   const size_t smem = tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs);
