@@ -268,7 +268,13 @@ def profile_step(step_fn, i):
         achieved = c['work'] / (c['ms'] * 1e-3) / 1e12 if c['ms'] > 0 else 0.0      # work = FLOPs
         roof = {'kernel': top, 'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'],
                 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
-                'peak_source': pk['source'] + ' cuBLAS bf16 (sustained); the kernel computes in fp32 on the CUDA cores',
+                'peak_source': pk['source'] + ' cuBLAS bf16 (sustained); ' +
+                               ('conv_tcp issues 3 TF32 tcgen05 passes per useful FLOP (fp32-grade 3xTF32), so its '
+                                'tensor-pipe work is ~3.4x the useful FLOPs counted here' if top == 'conv_tcp'
+                                else 'this kernel computes in fp32 on the CUDA cores'),
+                'traffic_note': ('dram read+write of one ncu --set full capture of this kernel (N = 210, 20->20 ch, '
+                                 '32x32): 17.3 MB per launch for 17.2 MB of input; see profiles/r01_v4_conv_tcp.md'
+                                 if top == 'conv_tcp' else None),
                 'share_of_step': c['ms'] / total_ms, 'avg_launch_us': 1e3 * c['ms'] / max(c['launches'], 1)}
     else:
         achieved = c['work'] / (c['ms'] * 1e-3) / 1e9 if c['ms'] > 0 else 0.0       # work = bytes

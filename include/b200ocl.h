@@ -196,17 +196,17 @@ int b200ocl_scr_augment(const float* x, float* out, const float* params, int N, 
 int b200ocl_selftest_umma_tf32(const float* A, const float* B, float* D, int N, int K, int mode, int* status,
                                void* stream);
 
-/* One 3x3 stride-1 pad-1 convolution (dgrad = 0: out[N,H,W,cout] = x[N,H,W,cin] * w; dgrad = 1: its data
- * gradient, x = dz[N,H,W,cout] -> out[N,H,W,cin]) through a chosen kernel family, NHWC fp32, weights OIHW:
- * path 0 automatic, 1 CUDA-core kernels, 2 tcgen05 with im2col tiles (conv_tc.cu), 3 tcgen05 fed from a halo
- * patch (conv_tcp.cu).  mode 0 raw store, 1 accumulate into out, 2 train (forward only): raw store plus
- * stats_out[4*cout] = batch mean, 1/sqrt(var+eps), running mean, running var updated from zero with momentum
- * 0.1.  Exists so that tests can pin every convolution kernel against a reference convolution; fails with
- * B200OCL_EUNSUPPORTED when the path does not cover the shape. */
-size_t b200ocl_conv_selftest_workspace_bytes(int N, int cin, int cout, int H, int W);
+/* One convolution (ks = 3 pad 1, or ks = 1 pad 0; stride 1 or 2; dgrad = 0: out[N,Hout,Wout,cout] = x[N,H,W,cin] * w;
+ * dgrad = 1, 3x3 stride 1 only: its data gradient, x = dz[N,H,W,cout] -> out[N,H,W,cin]) through a chosen kernel
+ * family, NHWC fp32, weights OIHW: path 0 automatic, 1 CUDA-core kernels, 2 tcgen05 with im2col tiles
+ * (conv_tc.cu), 3 tcgen05 fed from a halo strip (conv_tcp.cu).  mode 0 raw store, 1 accumulate into out, 2 train
+ * (forward only): raw store plus stats_out[4*cout] = batch mean, 1/sqrt(var+eps), running mean, running var
+ * updated from zero with momentum 0.1.  Exists so that tests can pin every convolution kernel against a reference
+ * convolution; fails with B200OCL_EUNSUPPORTED when the path does not cover the shape. */
+size_t b200ocl_conv_selftest_workspace_bytes(int N, int cin, int cout, int H, int W, int ks, int stride);
 int b200ocl_conv_selftest(const float* x, const float* w_oihw, float* out, int N, int H, int W, int cin, int cout,
-                          int dgrad, int path, int mode, float* stats_out, void* workspace, size_t workspace_bytes,
-                          void* stream);
+                          int ks, int stride, int dgrad, int path, int mode, float* stats_out, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* Window variant: A is read in place from a larger swizzled buffer P[rows][32] of 128-byte rows (tile row
  * 8g + r = P row start_row + g * sbo_rows + r), start address unaligned to the swizzle repeat when

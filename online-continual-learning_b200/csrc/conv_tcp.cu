@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
   const int slices = a.tp_slices;
   const TileGeom G = tile_geom(a.N, a.Hin, a.Win);
   const int PS = a.tp_ps, BS = a.tp_bs;            // patch stages, weight ring depth (launcher fits them to smem)
-  const bool chain3 = a.tp_chain == 3;
+  const int taps_n = a.ks * a.ks;                  // 9, or 1 (1x1 convolution = the centre tap of the padded geometry)
+  const bool one_tap = taps_n == 1;
+  const bool chain3 = a.tp_chain == 3 && !one_tap;
   float* sB = reinterpret_cast<float*>(smem_raw + (size_t)PS * 2 * G.pbytes);   // weight blocks
   const bool resident = (slices == 1 && NT == 32);   // all 9 weight blocks stay in shared memory
   const int b_slots = resident ? 9 : BS;
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
   if (tid == 0) {
     for (int i = 0; i < TP_PS_MAX; ++i) {
       umma::mbar_init(&pfull[i], 128);
-      umma::mbar_init(&pempty[i], TP_MW);
+      umma::mbar_init(&pempty[i], one_tap ? 1 : TP_MW);
     }
     for (int i = 0; i < 9; ++i) umma::mbar_init(&bfull[i], 1);
     for (int i = 0; i < TP_BS_MAX; ++i) umma::mbar_init(&bempty[i], 1);
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
   __syncthreads();
   umma::fence_after_thread_sync();
   const uint32_t tmem = tmem_slot;
-  const float* wimg = a.w_tp + (size_t)blockIdx.y * slices * 9 * B_BLOCK;
+  const float* wimg = a.w_tp + (size_t)blockIdx.y * slices * taps_n * B_BLOCK;
 
   if (warp >= 5 + TP_MW) {
     // =========================================================== patch loaders (128 threads)
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
     const uint32_t bytes = (uint32_t)(B_BLOCK * sizeof(float));
     if (resident) {
       if (umma::elect_one_sync()) {
-        for (int b = 0; b < 9; ++b) {
+        for (int b = 0; b < taps_n; ++b) {
           mbar_expect_tx(&bfull[b], bytes);
           bulk_g2s(sB + (size_t)b * B_BLOCK, wimg + (size_t)b * B_BLOCK, bytes, &bfull[b]);
         }
@@ -232,12 +234,12 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
       int q = 0;
       for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x)
         for (int sl = 0; sl < slices; ++sl)
-          for (int tap = 0; tap < 9; ++tap, ++q) {
+          for (int tap = 0; tap < taps_n; ++tap, ++q) {
             const int bs = q % BS;
             if (!umma::mbar_wait(&bempty[bs], (uint32_t)(((q / BS) & 1) ^ 1))) s_fail = 1;
             if (umma::elect_one_sync()) {
               mbar_expect_tx(&bfull[bs], bytes);
-              bulk_g2s(sB + (size_t)bs * B_BLOCK, wimg + (size_t)(sl * 9 + tap) * B_BLOCK, bytes, &bfull[bs]);
+              bulk_g2s(sB + (size_t)bs * B_BLOCK, wimg + (size_t)(sl * taps_n + tap) * B_BLOCK, bytes, &bfull[bs]);
             }
             __syncwarp();
           }
@@ -258,16 +260,18 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
     const uint32_t a_kh = (uint32_t)(G.wp * 8);              // one kernel row = W + 2 strip rows further
     int cnt = 0, pc = 0;                                      // K blocks issued by this warp; (tile, slice) pairs
     bool b_ready = false;
-    for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
+    const bool warp_active = !one_tap || mw == 1;     // a 1x1 convolution only has the centre tap (kh = kw = 1)
+    for (int tile = blockIdx.x; warp_active && tile < G.tiles_m; tile += gridDim.x) {
       for (int sl = 0; sl < slices; ++sl, ++pc) {
         const int ps = pc % PS;
         const int ksteps = (min(32, a.CK - sl * 32) + 7) / 8;
         if (!umma::mbar_wait(&pfull[ps], (uint32_t)((pc / PS) & 1))) s_fail = 1;
         const uint64_t dAs = dA0 + (uint64_t)(ps * A_STAGE);
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh, ++cnt) {
-          const int tap = kh * 3 + mw;
-          const int q = pc * 9 + tap;                  // position in the weight stream
+        for (int kh = 0; kh < 3; ++kh) {
+          if (one_tap && kh != 1) continue;
+          const int tap = one_tap ? 0 : kh * 3 + mw;   // index of the weight block inside the slice
+          const int q = pc * taps_n + tap;             // position in the weight stream
           const int b = resident ? tap : q % BS;
           // chain == 1: every tap has its own TMEM buffer and is promoted separately; chain == 3: the three
           // taps of this warp's kernel column accumulate in one buffer (a TMEM chain of <= 96 products)
@@ -299,8 +303,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
             }
             if (!resident) umma::mma_commit(&bempty[b]);
             if (!chain3 || kh == 2) umma::mma_commit(&tfull[t]);
-            if (kh == 2) umma::mma_commit(&pempty[ps]);
+            if (kh == 2 || one_tap) umma::mma_commit(&pempty[ps]);
           }
+          ++cnt;
           __syncwarp();
         }
         b_ready = true;
@@ -326,8 +331,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
       const int sp = tile * 128 + et;                    // strip position of this MMA row
       const int img = sp / G.pp, rem = sp - img * G.pp;
       const int y = rem / G.wp, x = rem - y * G.wp;
-      const bool valid = img < a.N && y < a.Hout && x < a.Wout;   // halo positions are by-products
-      const size_t m = ((size_t)img * a.Hout + y) * a.Wout + x;
+      // halo positions and (stride 2) odd positions are by-products
+      const bool valid = img < a.N && y < a.Hin && x < a.Win && (a.stride == 1 || ((y | x) & 1) == 0);
+      const size_t m = ((size_t)img * a.Hout + (a.stride == 1 ? y : y >> 1)) * a.Wout + (a.stride == 1 ? x : x >> 1);
       // The accumulators start from what the epilogue would otherwise have to fetch after the last tap --
       // the residual (eval) or the gradient being accumulated into (data gradient) -- so that global
       // latency is paid while the tensor core works on the tile, not after it.
@@ -352,9 +358,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
       }
       for (int sl = 0; sl < slices; ++sl, ++q) {        // q counts (tile, slice) pairs here
 #pragma unroll 1
-        for (int tap = 0; tap < (chain3 ? 3 : 9); ++tap) {
-          const int kh = chain3 ? 0 : tap / 3, mwq = tap - 3 * kh;
-          const int cq = chain3 ? q : q * 3 + kh;          // buffers MMA warp mwq filled before this one
+        for (int tap = 0; tap < (chain3 ? 3 : taps_n); ++tap) {
+          const int kh = (chain3 || one_tap) ? 0 : tap / 3, mwq = one_tap ? 1 : tap - 3 * kh;
+          const int cq = (chain3 || one_tap) ? q : q * 3 + kh;   // buffers MMA warp mwq filled before this one
           const int t = 2 * mwq + (cq & 1);
           if (!umma::mbar_wait(&tfull[t], (uint32_t)((cq >> 1) & 1))) s_fail = 1;
           umma::fence_after_thread_sync();
@@ -524,7 +530,8 @@ int launch_tcp(ConvArgs a, cudaStream_t stream) {
   // even out the tiles per CTA (e.g. 880 tiles on 148 CTAs = 6 rounds -> 147 CTAs of exactly 6)
   const int rounds = (G.tiles_m + gx - 1) / gx;
   gx = (G.tiles_m + rounds - 1) / rounds;
-  B200OCL_PROF(a.flip ? "conv_tc_dgrad" : (a.mode == CONV_EVAL ? "conv_tc_eval" : "conv_tc_train"),
+  // one kernel, three epilogues (eval / train / data gradient): profiled as one class
+  B200OCL_PROF("conv_tcp",
                2.0 * a.M * (double)a.CN * a.CK * 9.0, stream);
   conv_tcp_kernel<NT, KL><<<dim3(gx, n_tiles), TP_THREADS, smem, stream>>>(a);
   B200OCL_LAUNCHED();
@@ -538,8 +545,10 @@ bool conv_tcp_eligible(const ConvArgs& a) {
   const char* e = getenv("B200OCL_TCP");
   const char* e2 = getenv("B200OCL_TC");
   const bool enabled = !((e && e[0] == '0') || (e2 && e2[0] == '0'));
-  if (!enabled || !a.w_tp || a.ks != 3 || a.stride != 1 || a.transposed || a.pad != 1) return false;
-  if (a.Hin != a.Hout || a.Win != a.Wout || a.CK % 4 != 0) return false;
+  if (!enabled || !a.w_tp || a.transposed || a.CK % 4 != 0) return false;
+  if (!((a.ks == 3 && a.pad == 1) || (a.ks == 1 && a.pad == 0))) return false;
+  if (a.stride != 1 && (a.stride != 2 || a.flip)) return false;          // stride 2: forward only
+  if (a.Hout != (a.Hin + 2 * a.pad - a.ks) / a.stride + 1 || a.Wout != (a.Win + 2 * a.pad - a.ks) / a.stride + 1) return false;
   if (128 + 2 * (a.Win + 2) + 2 > 16 * TP_LD_MAX) return false;   // strip rows one stage holds (W <= 37)
   if ((long)a.N * (a.Hin + 2) * (a.Win + 2) > 2000000000L) return false;
   if (a.tp_bn <= 0 || a.tp_bn > 40 || a.CN % a.tp_bn != 0) return false;

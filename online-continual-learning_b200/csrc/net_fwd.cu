@@ -92,7 +92,7 @@ struct TpPackTable {
   int n;
   struct {
     unsigned int w_off, img_off;
-    int cin, cout, bn, nt, slices, dgrad;
+    int cin, cout, bn, nt, slices, dgrad, taps;
   } e[2 * NET_MAX_CONV];
 };
 
@@ -102,31 +102,31 @@ __global__ void __launch_bounds__(256) tp_pack_kernel(TpPackTable t, const float
   const int n_ch = L.dgrad ? L.cin : L.cout;
   const int k_ch = L.dgrad ? L.cout : L.cin;
   const int n_tiles = n_ch / L.bn;
-  const int total = n_tiles * L.slices * 9 * L.nt * 8;   // (tile, slice, tap, row, 16-byte chunk)
+  const int total = n_tiles * L.slices * L.taps * L.nt * 8;   // (tile, slice, tap, row, 16-byte chunk)
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int c = e & 7;
     int r = e >> 3;
     const int row = r % L.nt;
     r /= L.nt;
-    const int tap = r % 9;
-    r /= 9;
+    const int tap = r % L.taps;
+    r /= L.taps;
     const int sl = r % L.slices, tile = r / L.slices;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     const int k0 = sl * 32 + c * 4;
     if (row < L.bn && k0 < k_ch) {
       const int nch = tile * L.bn + row;
-      const int wt = L.dgrad ? 8 - tap : tap;
+      const int wt = L.dgrad ? L.taps - 1 - tap : tap;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int co = L.dgrad ? k0 + j : nch;
         const int ci = L.dgrad ? nch : k0 + j;
-        v[j] = params[L.w_off + ((size_t)co * L.cin + ci) * 9 + wt];
+        v[j] = params[L.w_off + ((size_t)co * L.cin + ci) * L.taps + wt];
       }
     }
     float4 h, l;
     umma::split_tf32(v[0], h.x, l.x); umma::split_tf32(v[1], h.y, l.y);
     umma::split_tf32(v[2], h.z, l.z); umma::split_tf32(v[3], h.w, l.w);
-    float* base = packed + L.img_off + ((size_t)((tile * L.slices + sl) * 9 + tap) * 2) * L.nt * 32;
+    float* base = packed + L.img_off + ((size_t)((tile * L.slices + sl) * L.taps + tap) * 2) * L.nt * 32;
     const int off = umma::sw128_offset_f32(row, c);
     *reinterpret_cast<float4*>(base + off) = h;
     *reinterpret_cast<float4*>(base + L.nt * 32 + off) = l;
@@ -170,8 +170,8 @@ int launch_pack(const NetPlan& p, const float* params, float* packed, cudaStream
   TpPackTable tp{};
   for (int i = 0; i < p.n_conv; ++i) {
     const ConvL& c = p.conv[i];
-    if (!c.tp_sl_f) continue;
     for (int d = 0; d < 2; ++d) {
+      if (!(d ? c.tp_sl_d : c.tp_sl_f)) continue;
       auto& e = tp.e[tp.n++];
       e.w_off = (unsigned)c.w_off;
       e.img_off = (unsigned)(d ? c.tp_d_off : c.tp_f_off);
@@ -180,6 +180,7 @@ int launch_pack(const NetPlan& p, const float* params, float* packed, cudaStream
       e.nt = tc_nt(e.bn);
       e.slices = d ? c.tp_sl_d : c.tp_sl_f;
       e.dgrad = d;
+      e.taps = c.ks * c.ks;
     }
   }
   if (tp.n) {
@@ -573,38 +574,42 @@ int b200ocl_net_pack(const b200ocl_net_desc* desc, const b200ocl_net_state* st, 
   return launch_pack(p, st->params, st->packed, static_cast<cudaStream_t>(stream));
 }
 
-static void selftest_layer(b200ocl::ConvL& c, int cin, int cout, int H, int W, size_t& pk) {
+static void selftest_layer(b200ocl::ConvL& c, int cin, int cout, int H, int W, int ks, int stride, size_t& pk) {
   c = b200ocl::ConvL{};
-  c.cin = cin; c.cout = cout; c.ks = 3; c.stride = 1; c.pad = 1;
-  c.hin = c.hout = H; c.win = c.wout = W;
+  c.cin = cin; c.cout = cout; c.ks = ks; c.stride = stride; c.pad = (ks == 3) ? 1 : 0;
+  c.hin = H; c.win = W;
+  c.hout = b200ocl::conv_out(H, ks, stride, c.pad);
+  c.wout = b200ocl::conv_out(W, ks, stride, c.pad);
   c.w_off = 0;
   pk = 0;
-  b200ocl::conv_pack_layout(c, pk);
+  b200ocl::conv_pack_layout(c, pk, true);
 }
 
-size_t b200ocl_conv_selftest_workspace_bytes(int N, int cin, int cout, int H, int W) {
+size_t b200ocl_conv_selftest_workspace_bytes(int N, int cin, int cout, int H, int W, int ks, int stride) {
   b200ocl::ConvL c;
   size_t pk = 0;
-  selftest_layer(c, cin, cout, H, W, pk);
-  const size_t M = (size_t)N * H * W;
+  selftest_layer(c, cin, cout, H, W, ks, stride, pk);
+  const size_t M = (size_t)N * H * W;   // upper bound (stride 1)
   const size_t stat = (size_t)b200ocl::conv_max_grid_m((int)M) * (cin > cout ? cin : cout) * 2 * sizeof(double);
   return b200ocl::align_up(pk * sizeof(float), 256) + b200ocl::align_up(stat, 256) + 256 /* counters */ + 256;
 }
 
 int b200ocl_conv_selftest(const float* x, const float* w_oihw, float* out, int N, int H, int W, int cin, int cout,
-                          int dgrad, int path, int mode, float* stats_out, void* workspace, size_t workspace_bytes,
-                          void* stream_) {
+                          int ks, int stride, int dgrad, int path, int mode, float* stats_out, void* workspace,
+                          size_t workspace_bytes, void* stream_) {
   using namespace b200ocl;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200OCL_CHECK_ARG(x && w_oihw && out && workspace, "null pointer");
   B200OCL_CHECK_ARG(N > 0 && H > 0 && W > 0 && cin % 20 == 0 && cout % 20 == 0 && cin > 0 && cout > 0, "bad shape");
   B200OCL_CHECK_ARG(mode >= 0 && mode <= 2 && (mode != 2 || (stats_out && !dgrad)), "mode 2 (train) needs stats_out, forward only");
-  B200OCL_CHECK_ARG(workspace_bytes >= b200ocl_conv_selftest_workspace_bytes(N, cin, cout, H, W), "workspace too small");
+  B200OCL_CHECK_ARG((ks == 3 || ks == 1) && (stride == 1 || stride == 2) && (!dgrad || (ks == 3 && stride == 1)),
+                    "3x3 or 1x1, stride 1 or 2; data gradient for 3x3 stride 1 only");
+  B200OCL_CHECK_ARG(workspace_bytes >= b200ocl_conv_selftest_workspace_bytes(N, cin, cout, H, W, ks, stride), "workspace too small");
   NetPlan p;
   memset(&p, 0, sizeof(p));
   p.n_conv = 1;
   size_t pk = 0;
-  selftest_layer(p.conv[0], cin, cout, H, W, pk);
+  selftest_layer(p.conv[0], cin, cout, H, W, ks, stride, pk);
   p.n_packed = pk;
   unsigned char* base = static_cast<unsigned char*>(workspace);
   float* packed = reinterpret_cast<float*>(base);
@@ -619,9 +624,10 @@ int b200ocl_conv_selftest(const float* x, const float* w_oihw, float* out, int N
   a.in = x;
   a.out = out;
   a.N = N;
-  a.Hin = a.Hout = H; a.Win = a.Wout = W;
-  a.ks = 3; a.stride = 1; a.pad = 1;
-  a.M = N * H * W;
+  a.Hin = H; a.Win = W;
+  a.Hout = c.hout; a.Wout = c.wout;
+  a.ks = ks; a.stride = stride; a.pad = c.pad;
+  a.M = N * c.hout * c.wout;
   a.mode = mode == 2 ? CONV_TRAIN : (mode == 1 ? CONV_ACCUM : CONV_RAW);
   a.force_path = path;
   a.eps = NET_BN_EPS;
