@@ -380,8 +380,8 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        steps, warmup = min(args.steps, 12), min(args.warmup, 1)
-        r = run_reference(args, steps, warmup, budget_s=120.0)
+        steps, warmup = min(args.steps, 40), min(args.warmup, 1)      # ~0.3 s per step on 16 cores
+        r = run_reference(args, steps, warmup, budget_s=90.0)
         steps = r['steps']
         line = {'impl': 'reference', 'metric': 'replay-step images/sec (ASER+SCR, ResNet18, CIFAR100)',
                 'value': r['value'], 'unit': 'stream images/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
@@ -403,7 +403,7 @@ def main():
     line = run_ours(args, rank, world)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            r = run_reference(args, 8, 1)
+            r = run_reference(args, 40, 1, budget_s=20.0)     # ~12 s of CPU work on 16 cores
             line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
         print(json.dumps(line))
     if world > 1:
