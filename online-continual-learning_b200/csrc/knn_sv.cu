@@ -123,7 +123,84 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_sv_kernel(KnnSvParams p) {
     const int row0 = tile * TE;
 
     // ------------------------------------------------------------------ phase 1: distances
-    for (int c0 = 0; c0 < CPAD; c0 += CT) {
+    // Wide variant for 513..1024 candidates (the memory-sweep shape): with TE = 16 the row-per-warp tiling
+    // below has only 2 x 8 pairs per thread for 10 shared-memory loads per feature (LSU-bound, measured 5x
+    // off the FMA bound).  Here warp w owns candidates [128w, 128w+128) for ALL 16 rows: 16 x 4 pairs per
+    // thread for five 16-byte loads per feature, operands prefetched into registers one 8-feature chunk ahead.
+    // Same per-pair fma order over the features, so the distances are bit-identical to the other tiling.
+    bool wide_done = false;
+    if constexpr (KPL == 32 && TE == 16) {
+      if (p.d % 8 == 0 && (reinterpret_cast<uintptr_t>(p.eval_f) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.cand_f) & 15) == 0) {
+        constexpr int DKW = 8;
+        float* se_w = se;   // [DKW][16]
+        float* sc_w = sc;   // [DKW][CPAD]   (8192 floats <= DK * (CT + 1))
+        float acc[16][4];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        float4 pc[8], pe = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto fetch = [&](int k0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int item = tid + KNN_THREADS * i;          // (candidate, half of the 8-feature chunk)
+            const int c = item >> 1, half = item & 1;
+            pc[i] = (c < p.C) ? __ldg(reinterpret_cast<const float4*>(p.cand_f + (size_t)c * p.d + k0 + half * 4))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (tid < 32) {
+            const int r = tid >> 1, half = tid & 1;
+            pe = (row0 + r < p.E) ? __ldg(reinterpret_cast<const float4*>(p.eval_f + (size_t)(row0 + r) * p.d + k0 + half * 4))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        fetch(0);
+        for (int k0 = 0; k0 < p.d; k0 += DKW) {
+          __syncthreads();   // previous chunk (and the previous tile's phase 3) fully consumed
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int item = tid + KNN_THREADS * i;
+            const int c = item >> 1, half = item & 1;
+            sc_w[(half * 4 + 0) * CPAD + c] = pc[i].x;
+            sc_w[(half * 4 + 1) * CPAD + c] = pc[i].y;
+            sc_w[(half * 4 + 2) * CPAD + c] = pc[i].z;
+            sc_w[(half * 4 + 3) * CPAD + c] = pc[i].w;
+          }
+          if (tid < 32) {
+            const int r = tid >> 1, half = tid & 1;
+            se_w[(half * 4 + 0) * 16 + r] = pe.x;
+            se_w[(half * 4 + 1) * 16 + r] = pe.y;
+            se_w[(half * 4 + 2) * 16 + r] = pe.z;
+            se_w[(half * 4 + 3) * 16 + r] = pe.w;
+          }
+          __syncthreads();
+          if (k0 + DKW < p.d) fetch(k0 + DKW);   // in flight during the arithmetic below
+#pragma unroll
+          for (int kk = 0; kk < DKW; ++kk) {
+            float a[16];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4)
+              *reinterpret_cast<float4*>(&a[4 * i4]) = *reinterpret_cast<const float4*>(se_w + kk * 16 + 4 * i4);
+            const float4 b4 = *reinterpret_cast<const float4*>(sc_w + kk * CPAD + warp * 128 + lane * 4);
+            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float df = a[i] - b[j];
+                acc[i][j] = fmaf(df, df, acc[i][j]);
+              }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sd[i * CPAD + swz<KPL>(warp * 128 + lane * 4 + j)] = acc[i][j];
+        __syncthreads();   // a warp sorts rows whose distances every warp contributed to
+        wide_done = true;
+      }
+    }
+    for (int c0 = 0; !wide_done && c0 < CPAD; c0 += CT) {
       float acc[TM][NJ];
 #pragma unroll
       for (int i = 0; i < TM; ++i)
