@@ -32,6 +32,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+WORKLOAD = ('ER+ASER replay step (asvm,k=3,n_smp_cls=1.5,10+10 imgs) + SCR replay step '
+            '(SupCon T=0.07,mlp head,10+100 imgs x 2 views), CIFAR-100 shapes, mem_size 5000, batch 10')
 MEM_SIZE = 5000
 BATCH = 10
 NUM_CLASSES = 100
@@ -180,13 +182,13 @@ def run_ours(args, rank, world):
     def timed(from_host):
         for i in range(args.warmup):
             step(i, from_host)
-        barrier()
         from b200ocl import engine as _eng
-        launches0 = _native.launch_count() + _eng.graph_launch_count()
         sampler = ClockSampler(local)
         if rank == 0:
-            sampler.start()
+            sampler.start()                           # BEFORE the barrier: spawning nvidia-smi must not delay rank 0's step 0
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        launches0 = _native.launch_count() + _eng.graph_launch_count()
         t0 = time.perf_counter()
         for k in range(args.steps):
             flush.fill_(k & 255)                      # L2 flush between timed iterations (outside the event pair)
@@ -196,16 +198,19 @@ def run_ours(args, rank, world):
         barrier()
         wall = time.perf_counter() - t0
         clocks = sampler.stop() if rank == 0 else None
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        per_step = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=dev)
+        t = torch.cat([per_step.sum().reshape(1), per_step])
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), _native.launch_count() + _eng.graph_launch_count() - launches0, clocks, wall
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)          # MAX over ranks of the sum and of every step
+        steps_ms = np.sort(t[1:].cpu().numpy())
+        stats = {'median_ms': float(np.median(steps_ms)), 'p10_ms': float(steps_ms[int(0.1 * (len(steps_ms) - 1))]),
+                 'p90_ms': float(steps_ms[int(round(0.9 * (len(steps_ms) - 1)))]), 'max_ms': float(steps_ms[-1])}
+        return float(t[0].item()), _native.launch_count() + _eng.graph_launch_count() - launches0, clocks, wall, stats
 
     log('rank %d: learners built' % rank)
-    ms_dev, launches, clocks, wall = timed(False)
+    ms_dev, launches, clocks, wall, stats = timed(False)
     log('rank %d: device-resident pass %.2f ms/step' % (rank, ms_dev / args.steps))
-    ms_e2e, _, _, _ = timed(True)
+    ms_e2e, _, _, _, stats_e2e = timed(True)
     log('rank %d: end-to-end pass %.2f ms/step' % (rank, ms_e2e / args.steps))
     if rank != 0:
         return None
@@ -222,11 +227,11 @@ def run_ours(args, rank, world):
         'unit': 'stream images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'ER+ASER replay step (asvm,k=3,n_smp_cls=1.5,10+10 imgs) + SCR replay step '
-                               '(SupCon T=0.07,mlp head,10+100 imgs x 2 views), CIFAR-100 shapes, mem_size 5000, batch 10',
+        'config': {'workload': WORKLOAD,
                    'stream_images_per_step': 2 * BATCH, 'trained_images_per_step': 20 + 110,
                    'parallelism': 'dp%d stream shards, NCCL grad all-reduce' % world if world > 1 else 'single GPU',
-                   'l2': 'flushed (256 MiB write) between timed steps', 'wall_s_timed_region': wall},
+                   'l2': 'flushed (256 MiB write) between timed steps', 'wall_s_timed_region': wall,
+                   'step_ms': stats, 'e2e_step_ms': stats_e2e},
         'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': 'stream images/s',
                 'h2d_bytes_per_step': 2 * (BATCH * 3 * 32 * 32 * 4 + BATCH * 8), 'd2h_bytes_per_step': 8},
         'gpu_launches': int(launches), 'clocks': clocks,
@@ -329,14 +334,61 @@ def log(msg):
 T0 = time.perf_counter()
 
 
+def run_reference_harness(device, steps, warmup, timeout_s=600):
+    """The UNMODIFIED reference agents (baseline/_ref, materialised by baseline/fetch_ref.py) through
+    baseline/ref_harness.py in a subprocess: --device cpu hides the GPUs so that every
+    torch.cuda.is_available() gate of the reference is off; --device cuda is the reference's own
+    single-GPU PyTorch path (cudnn.deterministic as general_main.py:15-18).  None if the tree is absent."""
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    try:
+        import ref_harness
+    finally:
+        sys.path.pop(0)
+    if ref_harness.locate() is None:
+        return None
+    cores = host_cores()
+    cmd = [sys.executable, os.path.join(ROOT, 'baseline', 'ref_harness.py'), '--device', device,
+           '--steps', str(steps), '--warmup', str(warmup), '--threads', str(cores)]
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
+        env.pop(k, None)
+    log('reference (%s) arm: %s' % (device, ' '.join(cmd[1:])))
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+    except subprocess.TimeoutExpired:
+        log('reference (%s) arm timed out' % device)
+        return None
+    if r.returncode != 0:
+        log('reference (%s) arm failed: %s' % (device, r.stderr[-2000:]))
+        return None
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    log('reference (%s) arm: ASER %.1f ms/step, SCR %.1f ms/step' % (device, out['aser_ms_per_step'], out['scr_ms_per_step']))
+    out['cores'] = cores
+    return out
+
+
 def run_reference(args, steps, warmup, budget_s=30.0):
-    """The reference's replay step on the host cores: oracle/replay_step.py (CPU, torch intra-op
-    threads = all cores).  Each step is one ER+ASER step and one SCR step like the CUDA arm."""
+    """The reference's replay step on the host cores.  Preferred: the unmodified reference itself
+    (kind "reference"); without baseline/_ref: oracle/replay_step.py, the restatement pinned against it
+    (kind "port").  Each step is one ER+ASER step and one SCR step like the CUDA arm."""
+    h = run_reference_harness('cpu', steps, warmup)
+    if h is not None:
+        return {'steps': steps, 'value': h['stream_images_per_s'], 'unit': 'stream images/s', 'cores': h['cores'],
+                'kind': 'reference',
+                'sample': '%d steps (one ER+ASER + one SCR replay step each) of the same workload after %d warm-up, '
+                          '%.1f s of CPU time, unmodified reference agents via train_learner (identity augmentation '
+                          'stub: kornia is absent), torch intra-op threads = %d'
+                          % (steps, max(warmup, 1), h['seconds'], h['threads']),
+                'ms_per_step': h['ms_per_step_pair'], 'aser_ms': h['aser_ms_per_step'], 'scr_ms': h['scr_ms_per_step']}
+    return run_reference_port(args, steps, warmup, budget_s)
+
+
+def run_reference_port(args, steps, warmup, budget_s=30.0):
     import torch
     from oracle import replay_step as ors
     cores = host_cores()
     torch.set_num_threads(cores)
-    log('reference arm: %d host cores (os.cpu_count()=%s)' % (cores, os.cpu_count()))
+    log('reference arm (port): %d host cores (os.cpu_count()=%s)' % (cores, os.cpu_count()))
     np.random.seed(0); torch.manual_seed(0)
     st_a, st_s = build_oracle_state('aser', 31), build_oracle_state('scr', 32)
     rs = np.random.RandomState(5)
@@ -348,7 +400,6 @@ def run_reference(args, steps, warmup, budget_s=30.0):
         ors.scr_step(st_s, xs, ys, eps_mem_batch=100, temperature=0.07)
     for _ in range(warmup):
         step()
-    log('reference arm: warm-up done')
     t0 = time.perf_counter()
     done = 0
     while done < steps:
@@ -358,7 +409,7 @@ def run_reference(args, steps, warmup, budget_s=30.0):
             break
     dt = time.perf_counter() - t0
     steps = done
-    log('reference arm: %d steps in %.1f s' % (steps, dt))
+    log('reference arm (port): %d steps in %.1f s' % (steps, dt))
     return {'steps': steps, 'value': 2 * BATCH * steps / dt, 'unit': 'stream images/s', 'cores': cores, 'kind': 'port',
             'sample': '%d steps (one ER+ASER + one SCR replay step each) of the same workload after %d warm-up, '
                       '%.1f s of CPU time, torch intra-op threads = %d' % (steps, warmup, dt, cores),
@@ -380,15 +431,16 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        steps, warmup = min(args.steps, 40), min(args.warmup, 1)      # ~0.3 s per step on 16 cores
+        os.environ['CUDA_VISIBLE_DEVICES'] = ''                      # the CPU arm never touches a GPU
+        steps, warmup = min(args.steps, 40), max(1, min(args.warmup, 2))   # ~0.4 s per step pair on 16 cores
         r = run_reference(args, steps, warmup, budget_s=90.0)
         steps = r['steps']
         line = {'impl': 'reference', 'metric': 'replay-step images/sec (ASER+SCR, ResNet18, CIFAR100)',
                 'value': r['value'], 'unit': 'stream images/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
                 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': 'ER+ASER replay step + SCR replay step, CIFAR-100 shapes, mem_size 5000, batch 10 '
-                                       '(reference algorithm, host CPU)', 'stream_images_per_step': 2 * BATCH},
+                'config': {'workload': WORKLOAD, 'stream_images_per_step': 2 * BATCH, 'trained_images_per_step': 20 + 110,
+                           'parallelism': 'host CPU, %d threads' % r['cores']},
                 'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
                 'e2e': {'value': r['value'], 'unit': 'stream images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                 'gpu_launches': 0}
@@ -403,8 +455,19 @@ def main():
     line = run_ours(args, rank, world)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            r = run_reference(args, 40, 1, budget_s=20.0)     # ~12 s of CPU work on 16 cores
+            r = run_reference(args, 30, 2, budget_s=20.0)     # ~12 s of CPU work on 16 cores
             line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+            g = run_reference_harness('cuda', 40, 5)          # the north-star's >=10x denominator
+            if g is not None:
+                line['reference_gpu'] = {
+                    'value': g['stream_images_per_s'], 'unit': 'stream images/s', 'ms_per_step': g['ms_per_step_pair'],
+                    'aser_ms': g['aser_ms_per_step'], 'scr_ms': g['scr_ms_per_step'],
+                    'what': 'unmodified reference agents (baseline/_ref) on cuda:0 of this box, torch %s eager, '
+                            'cudnn.deterministic=True, benchmark=False (general_main.py:15-18), same workload, '
+                            '40 steps after 5 warm-up, identity augmentation stub (kornia absent: the reference does '
+                            'less work than in production)' % g['torch']}
+                line['vs_reference_gpu'] = {'value_ratio': line['value'] / g['stream_images_per_s'],
+                                            'e2e_ratio': line['e2e']['value'] / g['stream_images_per_s']}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -17,6 +17,13 @@ void prof_begin(const char* kernel_class, double work, cudaStream_t stream);
 void prof_end();
 extern std::atomic<uint64_t> g_launches;
 int sm_count();
+// Function attributes (cudaFuncSetAttribute) are per device: every launcher keeps one flag per device.
+#define B200OCL_MAX_DEVICES 64
+inline int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= B200OCL_MAX_DEVICES) dev = 0;
+  return dev;
+}
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -568,7 +568,8 @@ int launch_conv_ksplit(const ConvArgs& a, cudaStream_t stream) {
   constexpr int BM = 32 * PT;
   constexpr int NST = (PT == 1 && KS == 4) ? 4 : 3;
   constexpr size_t smem = (size_t)(NST * KS * (BM * 20 + 400)) * sizeof(float) + 4 * BM * sizeof(int);
-  static bool configured = false;
+  static bool configured_dev[B200OCL_MAX_DEVICES] = {};
+  bool& configured = configured_dev[b200ocl::device_slot()];
   if (!configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(conv_ksplit_kernel<PT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
@@ -710,7 +711,8 @@ inline PatchTile patch_tile(const ConvArgs& a, int bn, int pt) {
 template <int BN, int PT>
 int launch_conv_patch(ConvArgs a, const PatchTile& t, cudaStream_t stream) {
   a.th = t.th; a.tw = t.tw; a.ti = t.ti;
-  static size_t configured = 0;
+  static size_t configured_dev[B200OCL_MAX_DEVICES] = {};
+  size_t& configured = configured_dev[b200ocl::device_slot()];
   if (t.smem > configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
     configured = t.smem;
@@ -727,7 +729,8 @@ template <int BN, int PT>
 int launch_conv_cfg(const ConvArgs& a, cudaStream_t stream) {
   constexpr int WN = BN / 20, WM = 4 / WN, BM = WM * 32 * PT;
   constexpr size_t smem = (size_t)(3 * BM * 20 + 3 * 20 * BN) * sizeof(float) + 4 * BM * sizeof(int);
-  static bool configured = false;
+  static bool configured_dev[B200OCL_MAX_DEVICES] = {};
+  bool& configured = configured_dev[b200ocl::device_slot()];
   if (!configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(conv_kernel<BN, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;

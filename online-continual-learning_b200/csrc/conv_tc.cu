@@ -583,7 +583,8 @@ __global__ void __launch_bounds__(416) conv_tc_ws_kernel(ConvArgs a) {
 template <int NT>
 int launch_tc_ws(const ConvArgs& a, cudaStream_t stream) {
   constexpr size_t smem = (size_t)3 * (2 * A_TILE + 2 * NT * 32) * sizeof(float) + 1024;
-  static bool configured = false;
+  static bool configured_dev[B200OCL_MAX_DEVICES] = {};
+  bool& configured = configured_dev[b200ocl::device_slot()];
   if (!configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(conv_tc_ws_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
@@ -599,7 +600,8 @@ int launch_tc_ws(const ConvArgs& a, cudaStream_t stream) {
 template <int NT>
 int launch_tc(const ConvArgs& a, cudaStream_t stream) {
   constexpr size_t smem = (size_t)2 * (2 * A_TILE + 2 * NT * 32) * sizeof(float) + 1024;
-  static bool configured = false;
+  static bool configured_dev[B200OCL_MAX_DEVICES] = {};
+  bool& configured = configured_dev[b200ocl::device_slot()];
   if (!configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;

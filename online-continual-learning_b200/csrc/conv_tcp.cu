@@ -517,7 +517,8 @@ int launch_tcp(ConvArgs a, cudaStream_t stream) {
   if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) a.tp_bs = 4;
   if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) { a.tp_ps = 2; a.tp_bs = 6; }
   const size_t smem = tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs);
-  static size_t configured = 0;
+  static size_t configured_dev[B200OCL_MAX_DEVICES] = {};
+  size_t& configured = configured_dev[b200ocl::device_slot()];
   if (smem > configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<NT, KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

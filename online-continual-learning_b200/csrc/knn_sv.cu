@@ -386,7 +386,8 @@ int launch_knn(const KnnSvParams& p0, cudaStream_t stream) {
   p.n_tiles = (p.E + TE - 1) / TE;
   int grid = p.n_tiles < knn_grid_cap() ? p.n_tiles : knn_grid_cap();
   if (grid < 1) grid = 1;
-  static bool configured = false;
+  static bool configured_dev[B200OCL_MAX_DEVICES] = {};
+  bool& configured = configured_dev[b200ocl::device_slot()];
   if (!configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(knn_sv_kernel<KPL, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;

@@ -669,7 +669,8 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     a.pix_per_split = g.pix_per_split;
     const size_t smem = (size_t)WG_NST * WG_MC * (g.kw * 128 + g.nw * 20) * sizeof(float) +
                         (size_t)(WG_NST + 1) * 3 * WG_MC * sizeof(int);
-    static bool configured = false;
+    static bool configured_dev[B200OCL_MAX_DEVICES] = {};
+  bool& configured = configured_dev[b200ocl::device_slot()];
     if (!configured) {
       B200OCL_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       configured = true;

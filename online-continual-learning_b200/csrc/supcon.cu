@@ -243,7 +243,8 @@ int b200ocl_supcon(const float* feats, const int64_t* labels, int B, int V, int 
   const size_t smem_grad = smem_stats + SC_WARPS * 32 * sizeof(float);
 
   B200OCL_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
-  static bool configured = false;
+  static bool configured_dev[B200OCL_MAX_DEVICES] = {};
+  bool& configured = configured_dev[b200ocl::device_slot()];
   if (!configured) {
     const int max_smem = 200 * 1024;  // d = 1024 needs 165 KB; static smem takes a little of the 227 KB
     B200OCL_CUDA(cudaFuncSetAttribute(supcon_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));

@@ -177,7 +177,8 @@ extern "C" int b200ocl_selftest_umma_tf32(const float* A, const float* B, float*
   B200OCL_CHECK_ARG(A && B && D && status, "null pointer");
   B200OCL_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && K >= 32 && K % 32 == 0, "need N in [16,256] %16, K %32");
   const size_t smem = (size_t)(2 * 128 * 32 + 2 * 256 * 32) * sizeof(float) + 1024;
-  static bool configured = false;
+  static bool configured_dev[B200OCL_MAX_DEVICES] = {};
+  bool& configured = configured_dev[b200ocl::device_slot()];
   if (!configured) {
     B200OCL_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;

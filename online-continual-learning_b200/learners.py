@@ -12,7 +12,7 @@ their forwards are kept for the BN side effect, their backwards are skipped.
 import numpy as np
 import torch
 
-from . import ops
+from . import memory, ops
 from .augment import SCRTransform
 from .engine import ce_loss
 from .memory import Buffer, input_size_match
@@ -47,7 +47,15 @@ class StreamFeeder(object):
     def __init__(self, x_train, y_train, batch, device):
         self.batch = batch
         y = np.asarray(y_train).astype(np.int64)
-        perm = torch.randperm(len(y)).numpy()            # DataLoader(shuffle=True) draws from the torch CPU generator
+        if memory.parity():
+            # the reference's DataLoader(shuffle=True, drop_last=True) itself, over slot numbers: consumes the
+            # default CPU generator exactly as exp_replay.py:21-23 / scr.py:29-31 do (base seed + sampler seed)
+            from torch.utils.data import DataLoader, TensorDataset
+            order = [b[0] for b in DataLoader(TensorDataset(torch.arange(len(y))), batch_size=batch, shuffle=True,
+                                              num_workers=0, drop_last=True)]
+            perm = torch.cat(order).numpy() if order else np.zeros(0, dtype=np.int64)
+        else:
+            perm = torch.randperm(len(y)).numpy()        # DataLoader(shuffle=True) draws from the torch CPU generator
         x = torch.from_numpy(np.ascontiguousarray(np.asarray(x_train)[perm]))
         if x.dtype == torch.uint8:
             x = x.to(device).permute(0, 3, 1, 2).to(torch.float32).div_(255.0).contiguous()
@@ -248,10 +256,10 @@ class ExperienceReplay(ContinualLearner):
 
     def train_learner(self, x_train, y_train):
         self.before_train(x_train, y_train)
-        stream = StreamFeeder(x_train, y_train, self.batch, self.device)
         self.model = self.model.train()
         meters = {k: AverageMeter() for k in ('losses_batch', 'losses_mem', 'acc_batch', 'acc_mem')}
         for ep in range(self.epoch):
+            stream = StreamFeeder(x_train, y_train, self.batch, self.device)   # DataLoader(shuffle=True): new order per epoch
             for i, (batch_x, batch_y, y_host) in enumerate(stream):
                 self.replay_step(batch_x, batch_y, y_host, meters if self.verbose else None)
                 if i % 100 == 1 and self.verbose:
@@ -297,10 +305,10 @@ class SupContrastReplay(ContinualLearner):
 
     def train_learner(self, x_train, y_train):
         self.before_train(x_train, y_train)
-        stream = StreamFeeder(x_train, y_train, self.batch, self.device)
         self.model = self.model.train()
         meters = {'losses': AverageMeter()}
         for ep in range(self.epoch):
+            stream = StreamFeeder(x_train, y_train, self.batch, self.device)   # DataLoader(shuffle=True): new order per epoch
             for i, (batch_x, batch_y, y_host) in enumerate(stream):
                 self.replay_step(batch_x, batch_y, y_host, meters if self.verbose else None)
                 if i % 100 == 1 and self.verbose:

@@ -8,10 +8,45 @@ Mirrors the reference surface (utils/buffer/buffer.py:8-41; utils/buffer/buffer_
     its class cache, buffer_utils.py:156-160);
   * rows move with the gather/scatter kernels of csrc/misc.cu.
 """
+import os
+from collections import defaultdict
+
 import numpy as np
 import torch
 
 from . import ops
+
+# --------------------------------------------------------------------------- parity mode
+# B200OCL_MODE=parity (or set_mode(True)) makes every random decision of the replay path consume the SAME
+# generators, with the same calls in the same order, as the reference: per-class torch.randperm on the
+# sampler's device in dict insertion order over Python sets built by the same add/remove history
+# (buffer_utils.py:105-113), the reservoir's float32 uniform_ on x's device (reservoir_update.py:35) and a
+# real DataLoader(shuffle=True) for the stream order.  A seeded reference run and a seeded b200ocl run then
+# retrieve and evict the same slots without injected choices.  It costs what the reference's version costs
+# (Python loops, device->host syncs), so it is a verification mode; the default mode draws from vectorised
+# host generators (statistically identical, not stream-identical).
+# B200OCL_PARITY_RNG=cpu pins the generators to the CPU (to replay a reference run that was recorded on a
+# machine without a GPU); default: the device the reference would use (cuda when available).
+_mode = {'parity': os.environ.get('B200OCL_MODE', '').lower() == 'parity',
+         'rng': os.environ.get('B200OCL_PARITY_RNG', '').lower()}
+
+
+def set_mode(parity, rng_device=None):
+    _mode['parity'] = bool(parity)
+    _mode['rng'] = (rng_device or '').lower()
+
+
+def parity():
+    return _mode['parity']
+
+
+def parity_rng_device(natural=None):
+    """Device of the reference's generator for a draw it makes on `natural` (default: its self.device)."""
+    if _mode['rng'] == 'cpu':
+        return torch.device('cpu')
+    if natural is not None:
+        return torch.device(natural)
+    return torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 
 input_size_match = {      # utils/setup_elements.py:11-17
     'cifar100': [3, 32, 32], 'cifar10': [3, 32, 32], 'core50': [3, 128, 128],
@@ -71,40 +106,58 @@ class _PinnedRing:
 
     def __init__(self, nbytes=1 << 20):
         self.nbytes = nbytes
+        self.half = nbytes // 2
         self.buf = None
-        self.off = 0
+        self.cur = 0                  # half being filled (tracked explicitly, never derived from an offset)
+        self.used = 0                 # bytes used in that half, 0..half
         self.events = [None, None]
 
     def _ensure(self):
         if self.buf is None:
             self.buf = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
 
+    # the three hooks tests replace to drive the ring without a GPU
+    def _alloc(self, shape, dtype, device):
+        return torch.empty(shape, dtype=dtype, device=device)
+
+    def _record(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
+
+    def _copy(self, out, view):
+        out.view(torch.uint8).reshape(-1).copy_(view, non_blocking=True)
+
+    def reserve(self, n):
+        """Byte offset of an n-byte slot (n <= half).  Leaving a half always records its event, entering
+        a half always waits for the event recorded when it was last left -- including when the
+        previous uploads ended exactly on the half boundary."""
+        need = (n + 15) // 16 * 16
+        if self.used + need > self.half:
+            self.events[self.cur] = self._record()
+            self.cur ^= 1
+            self.used = 0
+            if self.events[self.cur] is not None:
+                self.events[self.cur].synchronize()
+                self.events[self.cur] = None
+        off = self.cur * self.half + self.used
+        self.used += need
+        return off
+
     def upload(self, arr, device):
         arr = np.ascontiguousarray(arr)
         n = arr.nbytes
-        out = torch.empty(arr.shape, dtype=_TORCH_DTYPE[arr.dtype.type], device=device)
+        out = self._alloc(arr.shape, _TORCH_DTYPE[arr.dtype.type], device)
         if n == 0:
             return out
         self._ensure()
-        half = self.nbytes // 2
-        if n > half:      # large arrays bypass the ring
+        if n > self.half:      # large arrays bypass the ring
             out.copy_(torch.from_numpy(arr))
             return out
-        need = (n + 15) // 16 * 16
-        cur_half = self.off // half
-        if (self.off % half) + need > half:          # move to the other half
-            ev = torch.cuda.Event()
-            ev.record()
-            self.events[cur_half] = ev
-            cur_half ^= 1
-            self.off = cur_half * half
-            if self.events[cur_half] is not None:
-                self.events[cur_half].synchronize()
-                self.events[cur_half] = None
-        view = self.buf[self.off:self.off + n]
+        off = self.reserve(n)
+        view = self.buf[off:off + n]
         view.numpy()[:] = arr.reshape(-1).view(np.uint8)
-        self.off += need
-        out.view(torch.uint8).reshape(-1).copy_(view, non_blocking=True)
+        self._copy(out, view)
         return out
 
 
@@ -214,6 +267,8 @@ class ClassBalancedRandomSampling:
         flush_pending()
         if cls.labels_host is None:
             raise RuntimeError('ClassBalancedRandomSampling.update_cache has not been called')
+        if parity() and rng is None:
+            return cls._sample_indices_parity(int(n_smp_cls), excl_indices)
         rng = np.random if rng is None else rng
         n = int(n_smp_cls)
         cap = int(cls._cnt.max()) if cls._cnt.size else 0
@@ -236,6 +291,21 @@ class ClassBalancedRandomSampling:
         o = np.argsort(keys, axis=1, kind='stable')
         part, keys = np.take_along_axis(part, o, axis=1), np.take_along_axis(keys, o, axis=1)
         return cls._tab[np.arange(C)[:, None], part][keys < 2.0].astype(np.int64)
+
+    @classmethod
+    def _sample_indices_parity(cls, n, excl_indices):
+        """The reference's own loop (buffer_utils.py:100-113): classes in dict insertion order, the set
+        difference iterated in CPython set order, one torch.randperm per non-empty class on the sampler's
+        device.  One device -> host copy at the end."""
+        dev = parity_rng_device()
+        excl = set() if excl_indices is None else set(int(i) for i in np.asarray(list(excl_indices)).tolist())
+        parts = [torch.tensor([], device=dev, dtype=torch.long)]
+        for ind_set in cls.class_index_cache.values():
+            if ind_set:
+                valid_ind = ind_set - excl
+                perm_ind = torch.randperm(len(valid_ind), device=dev)
+                parts.append(torch.tensor(list(valid_ind), device=dev, dtype=torch.long)[perm_ind][:n])
+        return torch.cat(parts).cpu().numpy().astype(np.int64)
 
     @classmethod
     def sample(cls, buffer_x, buffer_y, n_smp_cls, excl_indices=None, device='cpu'):
@@ -305,6 +375,12 @@ class ClassBalancedRandomSampling:
                     cls._pos[members] = np.arange(k)
                     cache[c] = set(members.tolist())
                     start += k
+            if parity():
+                # the reference's rebuild (buffer_utils.py:156-160): classes keyed in order of first appearance,
+                # slots added in ascending order -- the dict / set iteration orders the parity sampler relies on
+                cache = defaultdict(set)
+                for i, c in enumerate(lab.tolist()):
+                    cache[c].add(i)
             cls.class_index_cache = cache
             # the reference leaves class_num_cache untouched on this path (buffer_utils.py:155-160)
 

@@ -8,6 +8,9 @@ import torch
 
 from . import _native
 
+KNN_MAX_CAND = 1024      # B200OCL_KNN_MAX_CAND (include/b200ocl.h)
+RANK_MAX = 4096          # b200ocl_rank_desc limit
+
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream

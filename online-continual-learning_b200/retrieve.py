@@ -37,6 +37,9 @@ class MIR_retrieve(object):
         self.params = params
         self.subsample = params.subsample
         self.num_retrieve = params.eps_mem_batch
+        if self.subsample > ops.RANK_MAX:
+            raise ValueError('MIR subsample %d exceeds the ranking kernel limit %d (b200ocl_rank_desc)'
+                             % (self.subsample, ops.RANK_MAX))
 
     def retrieve(self, buffer, **kwargs):
         sub_x, sub_y = random_retrieve(buffer, self.subsample)
@@ -80,6 +83,9 @@ class ASER_retrieve(object):
         self.n_smp_cls = int(params.n_smp_cls)
         self.out_dim = n_classes[params.data]
         self.is_aser_upt = params.update == 'ASER'
+        if self.n_smp_cls * self.out_dim > ops.KNN_MAX_CAND:
+            raise ValueError('ASER retrieve: n_smp_cls*num_classes = %d candidates exceed the kNN-SV kernel limit %d'
+                             % (self.n_smp_cls * self.out_dim, ops.KNN_MAX_CAND))
         ClassBalancedRandomSampling.reset()
 
     def retrieve(self, buffer, **kwargs):

@@ -17,9 +17,13 @@ def _host_labels(y, kwargs):
     return np.asarray(yh, dtype=np.int64)
 
 
-def reservoir_draws(n, n_seen):
-    """The reference draws float32 uniforms in [0, n_seen) and truncates (reservoir_update.py:35);
-    same call on the CPU generator (the reference draws on x's device)."""
+def reservoir_draws(n, n_seen, device=None):
+    """The reference draws float32 uniforms in [0, n_seen) and truncates (reservoir_update.py:35), on x's
+    device.  Default mode: the same call on the CPU generator (no device -> host sync in the step); parity
+    mode: the reference's call on the reference's device, then one copy to the host."""
+    if memory.parity() and device is not None:
+        dev = memory.parity_rng_device(device)
+        return torch.FloatTensor(n).to(dev).uniform_(0, n_seen).long().cpu().numpy()
     return torch.FloatTensor(n).uniform_(0, n_seen).long().numpy()
 
 
@@ -53,7 +57,7 @@ class Reservoir_update(object):
             if offset == batch_size:
                 return list(range(s, e))
         x, y, y_host = x[place_left:], y[place_left:], y_host[place_left:]
-        draws = reservoir_draws(x.size(0), buffer.n_seen_so_far)
+        draws = reservoir_draws(x.size(0), buffer.n_seen_so_far, x.device)
         self.last_draws = draws
         buffer.n_seen_so_far += x.size(0)
         slots, src = reservoir_plan(draws, mem)
@@ -88,6 +92,9 @@ class ASER_update(object):
         self.n_total_smp = int(params.n_smp_cls * self.out_dim)
         self.reservoir_update = Reservoir_update(params)
         self._last_decision = None
+        if self.n_total_smp + int(getattr(params, 'batch', 0)) > ops.KNN_MAX_CAND:
+            raise ValueError('ASER update: n_smp_cls*num_classes + batch = %d candidates exceed the kNN-SV kernel limit %d'
+                             % (self.n_total_smp + int(params.batch), ops.KNN_MAX_CAND))
         ClassBalancedRandomSampling.reset()
 
     def update(self, buffer, x, y, **kwargs):
