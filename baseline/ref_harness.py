@@ -56,7 +56,30 @@ def import_reference(path=None):
             setattr(sys.modules['kornia.augmentation'], n, Identity)
     import warnings
     warnings.filterwarnings('ignore')
+    _torch2_compat()
     return path
+
+
+def _torch2_compat():
+    """The reference pins torch 1.7.1 (requirements.txt:2).  Under torch >= 2 ONE statement of its GPU path
+    raises: aser_update.py:102 indexes the CPU index tensor that random_retrieve returns
+    (buffer_utils.py:17, torch.from_numpy) with a CUDA tensor.  The shim wraps the `random_retrieve` name
+    bound in utils.buffer.aser_update so that the returned indices live on the buffer's device -- same
+    values, same numpy draw, no file of the reference is edited.  It is a no-op on the CPU."""
+    import torch
+    from utils.buffer import aser_update
+    if getattr(aser_update.random_retrieve, '_b200ocl_compat', False):
+        return
+    orig = aser_update.random_retrieve
+
+    def random_retrieve(buffer, num_retrieve, excl_indices=None, return_indices=False):
+        out = orig(buffer, num_retrieve, excl_indices, return_indices)
+        if return_indices:
+            x, y, ind = out
+            return x, y, ind.to(buffer.buffer_img.device)
+        return out
+    random_retrieve._b200ocl_compat = True
+    aser_update.random_retrieve = random_retrieve
 
 
 def make_params(kind, **over):

@@ -289,6 +289,88 @@ def profile_step(step_fn, i):
     return {'roofline': roof, 'classes': {k: round(v['ms'], 4) for k, v in sorted(classes.items(), key=lambda kv: -kv[1]['ms'])}}
 
 
+
+# ----------------------------------------------------------------------------- kNN-SV sweep (BASELINE config 5)
+def run_knn_sweep(args, rank, world):
+    """`--workload knn_sweep`: 50 000 x 512 buffer features against 1 000 candidates, k = 3.  Eval rows (the
+    memory) are sharded across the ranks, the candidate block is replicated, each rank runs the fused kernel
+    on its shard and ONE NCCL all-gather moves the [3, C] column partials (sharded.knn_sv_sharded); every rank
+    combines them in rank order and ranks the candidates.  Strong scaling: the total work is fixed.
+    A step = one full sweep.  Rank 0 also runs the unsharded kernel and reports `ok`."""
+    import torch
+    import torch.distributed as dist
+    from b200ocl import ops, sharded
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    E, C, d, k = 50000, 1000, 512, 3
+    g = torch.Generator(device=dev).manual_seed(0)          # same data on every rank
+    ef = torch.relu(torch.randn(E, d, device=dev, generator=g))
+    cf = torch.relu(torch.randn(C, d, device=dev, generator=g))
+    ey = torch.randint(0, 100, (E,), device=dev, generator=g)
+    cy = torch.randint(0, 100, (C,), device=dev, generator=g)
+    lo, hi = sharded.shard_bounds(E, rank, world)
+    ef_l, ey_l = ef[lo:hi].contiguous(), ey[lo:hi].contiguous()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def sweep():
+        return sharded.aser_scores_sharded(ef_l, ey_l, E, cf, cy, k, 100)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        sweep()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 255)
+        ev[i][0].record()
+        top, red = sweep()
+        ev[i][1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    per = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=dev)
+    t = torch.cat([per.sum().reshape(1), per])
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    ms = float(t[0]) / args.steps
+    full = ops.knn_sv(ef, ey, cf, cy, k, want_sum=True, want_max=True, want_min=True)
+    err = float((full['sum'] - red['sum']).abs().max())
+    ok = err < 2e-4 and torch.equal(full['max'], red['max']) and torch.equal(full['min'], red['min'])
+    same = float((ops.rank_desc(full['sum'], 100) == top).float().mean())
+    pk = peaks()
+    alg_bytes = 4.0 * d * (E + C) + 8.0 * (E + C) + 4.0 * C * 3            # SURVEY 8(d): features + labels + 3 reductions
+    flops = 3.0 * E * C * d                                                 # direct-difference distances (sub, fma)
+    fp32_peak = 148 * 128 * 2 * (clocks['sm_max_mhz'] or 1965.0) * 1e6 / 1e12 if clocks else 74.4
+    steps_ms = np.sort(t[1:].cpu().numpy())
+    return {
+        'metric': 'kNN-SV sweep eval rows/sec (50k x 512 buffer features, 1k candidates, k=3)', 'value': E / (ms * 1e-3),
+        'unit': 'eval rows/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'ASER kNN-SV sweep: 50000 x 512 relu(N(0,1)) buffer features, 1000 candidates, labels U{0..99}, '
+                               'k=3, column sum/max/min + top-100; eval rows sharded over %d GPU(s), one NCCL all-gather of '
+                               '[3,1000] partials' % world,
+                   'l2': 'flushed (256 MiB write) between timed steps', 'step_ms': {'median': float(np.median(steps_ms)),
+                                                                                    'max': float(steps_ms[-1])}},
+        'ok': bool(ok), 'max_abs_err_vs_unsharded': err, 'top100_identical_fraction': same,
+        'roofline': {'kernel': 'knn_sv', 'bound': 'hbm', 'achieved': alg_bytes / (ms * 1e-3) / 1e9 / world,
+                     'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': alg_bytes / (ms * 1e-3) / 1e9 / world / pk['hbm_gbs'],
+                     'traffic': None, 'peak_source': pk['source'],
+                     'note': 'per-GPU algorithmic bytes / sweep time.  At d=512 the kernel is compute-bound (arithmetic '
+                             'intensity ~490 FLOP/B, SURVEY 7.3-1): see fp32_fma',
+                     'fp32_fma': {'achieved_tflops': flops / (ms * 1e-3) / 1e12 / world, 'peak_tflops': fp32_peak,
+                                  'frac': flops / (ms * 1e-3) / 1e12 / world / fp32_peak,
+                                  'peak_source': '148 SMs x 128 FMA lanes x 2 x max SM clock'}},
+        'gpu_launches': 2 * args.steps, 'clocks': clocks,
+    }
+
 # ----------------------------------------------------------------------------- CPU arm (reference algorithm)
 def build_oracle_state(kind, seed):
     import torch
@@ -423,6 +505,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='replay', choices=['replay', 'knn_sweep'])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     rank = int(os.environ.get('RANK', 0))
@@ -452,6 +535,13 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0))))
+    if args.workload == 'knn_sweep':
+        line = run_knn_sweep(args, rank, world)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     line = run_ours(args, rank, world)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -90,6 +90,11 @@ int b200ocl_supcon(const float* feats, const int64_t* labels, int B, int V, int 
 int b200ocl_gather_rows(const void* src, const int64_t* idx, int n_rows, size_t row_bytes, void* dst, void* stream);
 int b200ocl_scatter_rows(const void* src, const int64_t* idx, int n_rows, size_t row_bytes, void* dst, void* stream);
 
+/* Stream feeder (continuum/data_utils.py:38-54: ToTensor on every sample + DataLoader shuffle): dst[i] = image
+ * src[perm[i]] converted uint8 HWC -> fp32 CHW in [0,1] with an IEEE division by 255 (bit-identical to the
+ * reference's CPU ToTensor).  perm may be NULL (identity).  h*w*3 % 4 == 0. */
+int b200ocl_stream_prepare(const uint8_t* src_hwc, const int64_t* perm, int n, int h, int w, float* dst_chw, void* stream);
+
 /* ASER memory replacement on the device (reference utils/buffer/aser_update.py:88-112: current samples ranked
  * inside the first n_cand_buf places of the descending SV ranking replace, pairwise in rank order, the buffered
  * candidates ranked below).  order[n_total] ranks positions of [buffered candidates | current batch];

@@ -48,17 +48,8 @@ constexpr int TP_NB = 6;                            // TMEM accumulator buffers:
 constexpr int TP_BS_MAX = 6;                        // weight ring depth (streaming mode): 6 or 4
 constexpr int TP_LD_MAX = 13;                       // patch rows a loader thread stages per tile (16 rows per pass)
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(umma::smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-          umma::smem_u32(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"(umma::smem_u32(bar))
-      : "memory");
-}
+using umma::mbar_expect_tx;
+using umma::bulk_g2s;
 
 // acc += the NT fp32 columns of this warp's 32 TMEM lanes: all loads issued, one wait
 template <int NT>

@@ -161,6 +161,27 @@ __global__ void __launch_bounds__(256) sgd_kernel(const float* __restrict__ p, c
   }
 }
 
+
+// Stream feeder (continuum/data_utils.py:38-54 + ToTensor): image i of the output = source image perm[i],
+// uint8 HWC -> fp32 CHW, value / 255 with an IEEE division (bit-identical to torchvision's CPU ToTensor).
+// One CTA per image: coalesced word loads of the interleaved bytes into shared memory, planar coalesced stores.
+__global__ void __launch_bounds__(256) stream_prepare_kernel(const unsigned char* __restrict__ src,
+                                                             const long long* __restrict__ perm, float* __restrict__ dst,
+                                                             int hw) {
+  extern __shared__ __align__(16) unsigned char s_img[];
+  const size_t row = (size_t)hw * 3;
+  const unsigned char* in = src + (size_t)(perm ? perm[blockIdx.x] : blockIdx.x) * row;
+  const int words = (int)(row / 4);
+  for (int i = threadIdx.x; i < words; i += blockDim.x)
+    reinterpret_cast<unsigned int*>(s_img)[i] = __ldg(reinterpret_cast<const unsigned int*>(in) + i);
+  for (int i = words * 4 + threadIdx.x; i < (int)row; i += blockDim.x) s_img[i] = in[i];
+  __syncthreads();
+  float* out = dst + (size_t)blockIdx.x * row;
+  for (int o = threadIdx.x; o < (int)row; o += blockDim.x) {
+    const int c = o / hw, pix = o - c * hw;
+    out[o] = __fdiv_rn((float)s_img[pix * 3 + c], 255.f);
+  }
+}
 }  // namespace
 }  // namespace b200ocl
 
@@ -199,6 +220,27 @@ int b200ocl_scatter_rows(const void* src, const int64_t* idx, int n_rows, size_t
   B200OCL_CHECK_ARG(n_rows >= 0 && row_bytes % 4 == 0, "need n_rows >= 0 and row_bytes % 4 == 0");
   B200OCL_CHECK_ARG(n_rows == 0 || (src && idx && dst), "null pointer");
   return move_rows<true>(src, idx, n_rows, row_bytes, dst, static_cast<cudaStream_t>(stream));
+}
+
+int b200ocl_stream_prepare(const uint8_t* src_hwc, const int64_t* perm, int n, int h, int w, float* dst_chw, void* stream_) {
+  using namespace b200ocl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200OCL_CHECK_ARG(n >= 0 && h > 0 && w > 0, "need n >= 0 and positive h, w");
+  if (n == 0) return B200OCL_OK;
+  B200OCL_CHECK_ARG(src_hwc && dst_chw, "null pointer");
+  const size_t row = (size_t)h * w * 3;
+  B200OCL_CHECK_ARG(row % 4 == 0 && (reinterpret_cast<uintptr_t>(src_hwc) & 3) == 0, "image rows must be 4-byte aligned");
+  B200OCL_CHECK_ARG(row <= 200 * 1024, "image larger than shared memory");
+  static bool configured_dev[B200OCL_MAX_DEVICES] = {};
+  bool& configured = configured_dev[device_slot()];
+  if (!configured) {
+    B200OCL_CUDA(cudaFuncSetAttribute(stream_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  B200OCL_PROF("stream_prepare", 5.0 * n * (double)row, stream);
+  stream_prepare_kernel<<<n, 256, row, stream>>>(src_hwc, reinterpret_cast<const long long*>(perm), dst_chw, h * w);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
 }
 
 int b200ocl_aser_replace(const int64_t* order, int n_total, int n_cand_buf, const int64_t* cand_slot, const void* cur_x,

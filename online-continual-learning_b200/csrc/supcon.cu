@@ -1,8 +1,18 @@
 // supcon.cu -- fused supervised-contrastive loss, forward + backward (sm_100a).
 //
 // Replaces SupConLoss.forward and its autograd backward (utils/loss.py:19-96; ~40 ATen
-// kernels on [A,A] temporaries, A = V*B anchors) by two launches that never materialise the
-// [A,A] logit matrix:
+// kernels on [A,A] temporaries, A = V*B anchors).  The [A,A] logit matrix is never materialised.
+//
+// Main path (d % 4 == 0, d <= 256): ONE launch, supcon_fused_kernel.  Persistent CTAs own blocks of
+// TM anchors; contrast rows stream through a double-buffered shared-memory ring filled by TMA 1-D bulk
+// copies (cp.async.bulk + mbarrier, one row per copy into a padded pitch); the logit tile is a register-tiled
+// fp32 product (RM x RN outputs per thread, 128-bit shared loads along d); row statistics are reduced with
+// width-16 warp shuffles.  Phase A: online max / exp-sum / positive sums per anchor -> lse, |P(i)|, loss
+// partial.  One grid-wide arrive/wait (all CTAs are co-resident: grid <= SMs x occupancy).  Phase B: logits
+// recomputed, w_ij = (G_ij + G_ji)/T written transposed to shared memory, dC_i += W x C_j as a second
+// register-tiled product.  The loss is summed in unit order by CTA 0 (no float atomics anywhere).
+//
+// Fallback for other d (<= 1024): two launches,
 //   stats kernel  one warp per anchor i streams all contrast rows through shared memory,
 //                 lane j of a 32-row tile owns logit l_ij = c_i.c_j / T; online max /
 //                 exp-sum (diagonal in the max, out of the sum: loss.py:71-86), positive
@@ -16,12 +26,14 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace b200ocl {
 namespace {
 
 constexpr int SC_THREADS = 256;
 constexpr int SC_WARPS = 8;
+constexpr int SCF_MAX_D = 256;
 
 struct SupconParams {
   const float* feats;
@@ -34,6 +46,7 @@ struct SupconParams {
   unsigned int* counter;
   float* loss;
   float* dfeats;
+  int n_units;            // fused kernel: anchor blocks
 };
 
 __device__ __forceinline__ const float* anchor_row(const SupconParams& p, int a) {
@@ -196,6 +209,316 @@ __global__ void __launch_bounds__(SC_THREADS) supcon_grad_kernel(SupconParams p)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fused single-launch kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const float* anchor_row_ptr(const SupconParams& p, int a) {
+  const int v = a / p.B, b = a - v * p.B;
+  return p.feats + ((size_t)b * p.V + v) * p.d;
+}
+
+// warp 0: stage `rows` feature rows starting at anchor a0 into dst (pitch floats per row) with bulk copies
+__device__ __forceinline__ void stage_rows(const SupconParams& p, int a0, int rows, float* dst, int pitch, uint64_t* bar,
+                                           int lane) {
+  const int nvalid = max(0, min(rows, p.A - a0));
+  const uint32_t row_bytes = (uint32_t)p.d * 4u;
+  if (lane == 0) umma::mbar_expect_tx(bar, row_bytes * (uint32_t)nvalid);
+  __syncwarp();
+  for (int r = lane; r < nvalid; r += 32) umma::bulk_g2s(dst + (size_t)r * pitch, anchor_row_ptr(p, a0 + r), row_bytes, bar);
+}
+
+// every CTA arrives once; valid because the whole grid is co-resident
+__device__ __forceinline__ void grid_arrive_wait(unsigned int* counter, unsigned int expected) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.u32 %0, [%1];\n" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < expected);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int RM, int RN>
+__device__ __forceinline__ void logit_tile(const float* __restrict__ sA, const float* __restrict__ sBt, int P, int d,
+                                           int ty, int tx, float inv_is_div_T, float (&l)[RM][RN]) {
+#pragma unroll
+  for (int r = 0; r < RM; ++r)
+#pragma unroll
+    for (int c = 0; c < RN; ++c) l[r][c] = 0.f;
+  const float* ap = sA + (size_t)(ty * RM) * P;
+  const float* bp = sBt + (size_t)tx * P;
+#pragma unroll 2
+  for (int k = 0; k < d; k += 4) {
+    float4 a[RM], b[RN];
+#pragma unroll
+    for (int r = 0; r < RM; ++r) a[r] = *reinterpret_cast<const float4*>(ap + (size_t)r * P + k);
+#pragma unroll
+    for (int c = 0; c < RN; ++c) b[c] = *reinterpret_cast<const float4*>(bp + (size_t)(16 * c) * P + k);
+#pragma unroll
+    for (int r = 0; r < RM; ++r)
+#pragma unroll
+      for (int c = 0; c < RN; ++c) {
+        l[r][c] = fmaf(a[r].x, b[c].x, l[r][c]);
+        l[r][c] = fmaf(a[r].y, b[c].y, l[r][c]);
+        l[r][c] = fmaf(a[r].z, b[c].z, l[r][c]);
+        l[r][c] = fmaf(a[r].w, b[c].w, l[r][c]);
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < RM; ++r)
+#pragma unroll
+    for (int c = 0; c < RN; ++c) l[r][c] = __fdiv_rn(l[r][c], inv_is_div_T);   // torch.div(anchor_dot_contrast, T), loss.py:67-69
+}
+
+template <int RM, int RN, int NC>
+__global__ void __launch_bounds__(SC_THREADS, 1) supcon_fused_kernel(SupconParams p) {
+  constexpr int TM = 16 * RM, TN = 16 * RN, WP = TM + 4;
+  extern __shared__ __align__(128) unsigned char raw[];
+  const int P = p.d + 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw);          // [0] anchors, [1],[2] contrast ring
+  float* sA = reinterpret_cast<float*>(raw + 128);
+  float* sB = sA + (size_t)TM * P;                            // [2][TN][P]
+  float* sWt = sB + (size_t)2 * TN * P;                       // [TN][WP]
+  long long* sLab = reinterpret_cast<long long*>(sWt + (size_t)TN * WP);   // [2][TN]
+  float* sLse = reinterpret_cast<float*>(sLab + 2 * TN);      // [2][TN]
+  float* sNp = sLse + 2 * TN;                                 // [2][TN]
+  float* sRow = sNp + 2 * TN;                                 // [TM] per-anchor loss terms
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int n_tiles = (p.A + TN - 1) / TN;
+  const float invA = 1.f / (float)p.A;
+
+  // zero the staging buffers once: rows past A are never written by a copy and must stay finite
+  for (int idx = tid; idx < (TM + 2 * TN) * P; idx += SC_THREADS) sA[idx] = 0.f;
+  if (tid == 0) {
+    umma::mbar_init(&bars[0], 1);
+    umma::mbar_init(&bars[1], 1);
+    umma::mbar_init(&bars[2], 1);
+    umma::fence_mbar_init();
+  }
+  umma::fence_proxy_async_smem();
+  __syncthreads();
+  uint32_t a_phase = 0, b_count = 0;      // b_count: contrast tiles consumed so far (ring slot = count & 1)
+
+  for (int phase = 0; phase < 2; ++phase) {
+    if (phase == 1) {
+      if (!p.dfeats) break;
+      grid_arrive_wait(p.counter, gridDim.x);
+    }
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+      const int i0 = unit * TM;
+      if (warp == 0) {
+        stage_rows(p, i0, TM, sA, P, &bars[0], lane);
+        stage_rows(p, 0, TN, sB + (size_t)(b_count & 1) * TN * P, P, &bars[1 + (b_count & 1)], lane);
+      }
+      long long yi[RM];
+      float lse_i[RM], np_i[RM];
+      int gi[RM];
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        gi[r] = i0 + ty * RM + r;
+        const bool v = gi[r] < p.A;
+        yi[r] = v ? p.labels[gi[r] % p.B] : 0;
+        lse_i[r] = (phase == 1 && v) ? __ldcg(p.lse + gi[r]) : 0.f;
+        np_i[r] = (phase == 1 && v) ? __ldcg(p.npos + gi[r]) : 1.f;
+      }
+      float m[RM], z[RM], ps[RM], np[RM];
+      float acc[RM][NC * 4];
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        m[r] = -FLT_MAX; z[r] = 0.f; ps[r] = 0.f; np[r] = 0.f;
+#pragma unroll
+        for (int q = 0; q < NC * 4; ++q) acc[r][q] = 0.f;
+      }
+      umma::mbar_wait(&bars[0], a_phase);
+      a_phase ^= 1;
+
+      for (int t = 0; t < n_tiles; ++t, ++b_count) {
+        const int slot = b_count & 1;
+        const int j0 = t * TN;
+        float* sBt = sB + (size_t)slot * TN * P;
+        if (warp == 0 && t + 1 < n_tiles)
+          stage_rows(p, j0 + TN, TN, sB + (size_t)(slot ^ 1) * TN * P, P, &bars[1 + (slot ^ 1)], lane);
+        if (tid < TN) {
+          const int j = j0 + tid;
+          const bool v = j < p.A;
+          sLab[slot * TN + tid] = v ? p.labels[j % p.B] : 0;
+          if (phase == 1) {
+            sLse[slot * TN + tid] = v ? __ldcg(p.lse + j) : 0.f;
+            sNp[slot * TN + tid] = v ? __ldcg(p.npos + j) : 1.f;
+          }
+        }
+        umma::mbar_wait(&bars[1 + slot], (b_count >> 1) & 1);
+        __syncthreads();
+
+        float l[RM][RN];
+        logit_tile<RM, RN>(sA, sBt, P, p.d, ty, tx, p.T, l);
+
+        if (phase == 0) {
+#pragma unroll
+          for (int r = 0; r < RM; ++r) {
+            float tm = -FLT_MAX;
+#pragma unroll
+            for (int c = 0; c < RN; ++c)
+              if (j0 + tx + 16 * c < p.A) tm = fmaxf(tm, l[r][c]);     // the diagonal takes part in the max (loss.py:71)
+            if (tm > m[r]) {
+              z[r] *= __expf(m[r] - tm);
+              m[r] = tm;
+            }
+#pragma unroll
+            for (int c = 0; c < RN; ++c) {
+              const int j = j0 + tx + 16 * c;
+              if (j < p.A && j != gi[r]) {
+                z[r] += __expf(l[r][c] - m[r]);
+                if (sLab[slot * TN + tx + 16 * c] == yi[r]) {
+                  ps[r] += l[r][c];
+                  np[r] += 1.f;
+                }
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < RM; ++r)
+#pragma unroll
+            for (int c = 0; c < RN; ++c) {
+              const int jl = tx + 16 * c, j = j0 + jl;
+              float w = 0.f;
+              if (j < p.A && gi[r] < p.A && j != gi[r]) {
+                const float pos = (sLab[slot * TN + jl] == yi[r]) ? 1.f : 0.f;
+                const float g_ij = __expf(l[r][c] - lse_i[r]) - pos / np_i[r];
+                const float g_ji = __expf(l[r][c] - sLse[slot * TN + jl]) - pos / sNp[slot * TN + jl];
+                w = (g_ij + g_ji) * invA / p.T;
+              }
+              sWt[jl * WP + ty * RM + r] = w;
+            }
+          __syncthreads();
+          const int jn = min(TN, p.A - j0);
+          const float* wp = sWt + ty * RM;
+#pragma unroll 4
+          for (int jj = 0; jj < jn; ++jj) {
+            float wv[RM];
+#pragma unroll
+            for (int r = 0; r < RM; ++r) wv[r] = wp[jj * WP + r];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              const int dd = (tx + 16 * c) * 4;
+              if (dd < p.d) {
+                const float4 cv = *reinterpret_cast<const float4*>(sBt + (size_t)jj * P + dd);
+#pragma unroll
+                for (int r = 0; r < RM; ++r) {
+                  acc[r][c * 4 + 0] = fmaf(wv[r], cv.x, acc[r][c * 4 + 0]);
+                  acc[r][c * 4 + 1] = fmaf(wv[r], cv.y, acc[r][c * 4 + 1]);
+                  acc[r][c * 4 + 2] = fmaf(wv[r], cv.z, acc[r][c * 4 + 2]);
+                  acc[r][c * 4 + 3] = fmaf(wv[r], cv.w, acc[r][c * 4 + 3]);
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();            // sB[slot], sWt and the per-tile arrays are free for the next stage
+      }
+
+      if (phase == 0) {
+        // combine the 16 lanes that share a row (xor 8,4,2,1 stays inside a half-warp)
+#pragma unroll
+        for (int r = 0; r < RM; ++r) {
+          float M = m[r];
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(FULL_MASK, M, o));
+          float Z = z[r] * __expf(m[r] - M), PS = ps[r], NP = np[r];
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {
+            Z += __shfl_xor_sync(FULL_MASK, Z, o);
+            PS += __shfl_xor_sync(FULL_MASK, PS, o);
+            NP += __shfl_xor_sync(FULL_MASK, NP, o);
+          }
+          if (tx == 0) {
+            float li = 0.f;
+            if (gi[r] < p.A) {
+              const float lse = M + logf(Z);
+              li = -(PS - NP * lse) / NP;               // 0/0 -> NaN like loss.py:90
+              p.lse[gi[r]] = lse;
+              p.npos[gi[r]] = NP;
+            }
+            sRow[ty * RM + r] = li;
+          }
+        }
+        __syncthreads();
+        if (tid == 0) {
+          float tsum = 0.f;
+          for (int r = 0; r < TM; ++r) tsum += sRow[r];
+          p.part[unit] = tsum;
+        }
+        __syncthreads();
+      } else {
+#pragma unroll
+        for (int r = 0; r < RM; ++r) {
+          if (gi[r] >= p.A) continue;
+          const int v = gi[r] / p.B, b = gi[r] - v * p.B;
+          float* out = p.dfeats + ((size_t)b * p.V + v) * p.d;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const int dd = (tx + 16 * c) * 4;
+            if (dd < p.d)
+              *reinterpret_cast<float4*>(out + dd) = make_float4(acc[r][c * 4], acc[r][c * 4 + 1], acc[r][c * 4 + 2], acc[r][c * 4 + 3]);
+          }
+        }
+      }
+    }
+    if (phase == 0 && !p.dfeats) grid_arrive_wait(p.counter, gridDim.x);   // loss needs every unit's partial
+    if (phase == 0 && p.dfeats) continue;
+  }
+  // after the grid-wide wait every partial is visible: CTA 0 adds them in unit order
+  if (blockIdx.x == 0 && tid == 0) {
+    double t = 0.0;
+    for (int u = 0; u < p.n_units; ++u) t += (double)__ldcg(p.part + u);
+    *p.loss = (float)(t / (double)p.A);
+  }
+}
+
+template <int RM, int RN, int NC>
+int launch_fused(SupconParams p, cudaStream_t stream) {
+  constexpr int TM = 16 * RM, TN = 16 * RN, WP = TM + 4;
+  const int P = p.d + 4;
+  const size_t smem = 128 + (size_t)(TM + 2 * TN) * P * 4 + (size_t)TN * WP * 4 + (size_t)2 * TN * 8 + (size_t)4 * TN * 4 +
+                      (size_t)TM * 4;
+  static int coresident_dev[B200OCL_MAX_DEVICES] = {};
+  int& coresident = coresident_dev[device_slot()];
+  if (coresident == 0) {
+    B200OCL_CUDA(cudaFuncSetAttribute(supcon_fused_kernel<RM, RN, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int per_sm = 0;
+    B200OCL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, supcon_fused_kernel<RM, RN, NC>, SC_THREADS, smem));
+    if (per_sm < 1) {
+      set_error("b200ocl_supcon: fused kernel does not fit on an SM (smem %zu)", smem);
+      return B200OCL_EUNSUPPORTED;
+    }
+    coresident = sm_count();          // one CTA per SM: the grid-wide wait needs every CTA resident
+  }
+  p.n_units = (p.A + TM - 1) / TM;
+  const int grid = p.n_units < coresident ? p.n_units : coresident;
+  B200OCL_PROF("supcon", 2.0 * 4.0 * p.A * p.d + 8.0 * p.B, stream);
+  supcon_fused_kernel<RM, RN, NC><<<grid, SC_THREADS, smem, stream>>>(p);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
+
+template <int RM, int RN>
+int launch_fused_nc(const SupconParams& p, cudaStream_t stream) {
+  switch ((p.d + 63) / 64) {
+    case 1: return launch_fused<RM, RN, 1>(p, stream);
+    case 2: return launch_fused<RM, RN, 2>(p, stream);
+    case 3: return launch_fused<RM, RN, 3>(p, stream);
+    default: return launch_fused<RM, RN, 4>(p, stream);
+  }
+}
+
 }  // namespace
 }  // namespace b200ocl
 
@@ -243,6 +566,13 @@ int b200ocl_supcon(const float* feats, const int64_t* labels, int B, int V, int 
   const size_t smem_grad = smem_stats + SC_WARPS * 32 * sizeof(float);
 
   B200OCL_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
+  if (d % 4 == 0 && d <= SCF_MAX_D && (reinterpret_cast<uintptr_t>(feats) & 15) == 0 &&
+      (!dfeats || (reinterpret_cast<uintptr_t>(dfeats) & 15) == 0)) {
+    const int sms = sm_count();
+    if (p.A <= 16 * sms) return launch_fused_nc<1, 2>(p, stream);
+    if (p.A <= 32 * sms) return launch_fused_nc<2, 4>(p, stream);
+    return launch_fused_nc<4, 4>(p, stream);
+  }
   static bool configured_dev[B200OCL_MAX_DEVICES] = {};
   bool& configured = configured_dev[b200ocl::device_slot()];
   if (!configured) {

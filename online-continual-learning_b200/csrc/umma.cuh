@@ -87,6 +87,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- TMA 1-D bulk copy global -> shared (cp.async.bulk, UBLKCP in SASS); completion counted in bytes on an mbarrier.
+// dst / src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // ---- one elected lane of a converged warp.  Unlike `lane == 0`, the elect.sync predicate keeps the region
 // warp-uniform for ptxas: tcgen05 / bulk-copy instructions inside are emitted once, without the per-active-lane
 // ELECT / BRA.U.ANY loops a divergent branch needs around every uniform-datapath instruction.

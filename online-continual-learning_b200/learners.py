@@ -56,11 +56,14 @@ class StreamFeeder(object):
             perm = torch.cat(order).numpy() if order else np.zeros(0, dtype=np.int64)
         else:
             perm = torch.randperm(len(y)).numpy()        # DataLoader(shuffle=True) draws from the torch CPU generator
-        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x_train)[perm]))
-        if x.dtype == torch.uint8:
-            x = x.to(device).permute(0, 3, 1, 2).to(torch.float32).div_(255.0).contiguous()
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x_train)))
+        if x.dtype == torch.uint8 and torch.device(device).type == 'cuda':
+            # one upload of the raw bytes, then shuffle + HWC->CHW + /255 in one kernel (csrc/misc.cu)
+            x = ops.stream_prepare(x.to(device), torch.from_numpy(perm).to(device))
+        elif x.dtype == torch.uint8:
+            x = x[torch.from_numpy(perm)].permute(0, 3, 1, 2).to(torch.float32).div_(255.0).contiguous()
         else:                                             # already float NCHW
-            x = x.to(device=device, dtype=torch.float32).contiguous()
+            x = x[torch.from_numpy(perm)].to(device=device, dtype=torch.float32).contiguous()
         self.x = x
         self.y_host = y[perm]
         self.y = torch.from_numpy(self.y_host).to(device)

@@ -136,6 +136,21 @@ def gather_rows(src, idx, out=None):
     return out
 
 
+def stream_prepare(x_u8_nhwc, perm=None):
+    """uint8 [n,H,W,3] (device) -> fp32 [n,3,H,W] in [0,1], rows taken in `perm` order (ToTensor + shuffle)."""
+    _need_cuda(x_u8_nhwc, perm)
+    if x_u8_nhwc.dtype != torch.uint8 or x_u8_nhwc.dim() != 4 or x_u8_nhwc.shape[3] != 3:
+        raise ValueError('expected uint8 images [n,H,W,3]')
+    x = x_u8_nhwc.contiguous()
+    n, h, w = (perm.numel() if perm is not None else x.shape[0]), x.shape[1], x.shape[2]
+    out = torch.empty((n, 3, h, w), dtype=torch.float32, device=x.device)
+    if perm is not None:
+        perm = _i64(perm).reshape(-1)
+    rc = _native.lib().b200ocl_stream_prepare(_ptr(x), _ptr(perm), n, h, w, _ptr(out), _stream())
+    _native.check(rc, 'b200ocl_stream_prepare')
+    return out
+
+
 def scatter_rows(dst, idx, src):
     """dst[idx[i]] = src[i] over the first dimension (buffer_img[idx] = x)."""
     _need_cuda(dst, idx, src)

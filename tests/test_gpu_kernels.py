@@ -179,7 +179,12 @@ def test_supcon_golden_and_oracle(ops, golden_dir):
 
 
 @pytest.mark.parametrize('B,V,d,T', [(110, 2, 128, 0.07), (7, 2, 33, 0.1), (1024, 2, 128, 0.07), (40, 3, 200, 0.5),
-                                     (16, 2, 600, 0.07), (3, 1, 1024, 1.0)])
+                                     (16, 2, 600, 0.07), (3, 1, 1024, 1.0),
+                                     # the fused single-launch kernel: every tile configuration (TM 16 / 32 / 64),
+                                     # every d chunk count, ragged last tiles, a unit count above the SM count
+                                     (110, 2, 160, 0.07), (50, 2, 256, 0.1), (9, 1, 4, 0.2), (33, 3, 64, 0.07),
+                                     (1300, 2, 128, 0.07), (1250, 2, 160, 0.1), (2500, 2, 128, 0.07),
+                                     (2400, 2, 256, 0.07), (4801, 2, 64, 0.07)])
 def test_supcon_shapes(ops, B, V, d, T):
     rs = np.random.RandomState(B + d)
     f = rs.standard_normal((B, V, d)).astype(np.float32)
@@ -227,3 +232,20 @@ def test_rows_and_sgd(ops):
     torch.testing.assert_close(out, p - 0.1 * gr, rtol=1e-6, atol=1e-7)
     ops.sgd_step(p, gr, 0.05, 1e-4, out=out)
     torch.testing.assert_close(out, p - 0.05 * (gr + 1e-4 * p), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('n,hw', [(57, 32), (9, 84), (3, 50)])
+def test_stream_prepare_matches_totensor(ops, n, hw):
+    """uint8 HWC -> fp32 CHW /255 + shuffle, bit-identical to torchvision's ToTensor on the CPU
+    (continuum/data_utils.py:38-54; utils/setup_elements.py:29-43)."""
+    from torchvision import transforms
+    rs = np.random.RandomState(n)
+    x = rs.randint(0, 256, (n, hw, hw, 3)).astype(np.uint8)
+    x[0] = 255; x[1] = 0
+    perm = rs.permutation(n)[: n - 2]
+    got = ops.stream_prepare(torch.from_numpy(x).cuda(), torch.from_numpy(perm).cuda()).cpu()
+    tt = transforms.ToTensor()
+    ref = torch.stack([tt(x[i]) for i in perm])
+    assert torch.equal(got, ref)
+    ident = ops.stream_prepare(torch.from_numpy(x).cuda()).cpu()
+    assert torch.equal(ident, torch.stack([tt(x[i]) for i in range(n)]))
