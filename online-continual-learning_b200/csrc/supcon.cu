@@ -245,7 +245,7 @@ __device__ __forceinline__ void grid_arrive_wait(unsigned int* counter, unsigned
 
 template <int RM, int RN>
 __device__ __forceinline__ void logit_tile(const float* __restrict__ sA, const float* __restrict__ sBt, int P, int d,
-                                           int ty, int tx, float inv_is_div_T, float (&l)[RM][RN]) {
+                                           int ty, int tx, float inv_T, float (&l)[RM][RN]) {
 #pragma unroll
   for (int r = 0; r < RM; ++r)
 #pragma unroll
@@ -272,30 +272,35 @@ __device__ __forceinline__ void logit_tile(const float* __restrict__ sA, const f
 #pragma unroll
   for (int r = 0; r < RM; ++r)
 #pragma unroll
-    for (int c = 0; c < RN; ++c) l[r][c] = __fdiv_rn(l[r][c], inv_is_div_T);   // torch.div(anchor_dot_contrast, T), loss.py:67-69
+    for (int c = 0; c < RN; ++c) l[r][c] *= inv_T;   // anchor_dot_contrast / T (loss.py:67-69) as a product with fl(1/T): <= 1 ulp apart
 }
 
-template <int RM, int RN, int NC>
+// RES: the whole contrast set (all n_tiles x TN rows) is resident in shared memory, staged once with one
+// mbarrier -- the shape of the replay path itself (A = 220 anchors, d = 128: 113 KB).  Otherwise rows stream
+// through a two-slot ring, tile t+1 in flight while tile t is consumed.
+template <int RM, int RN, int NC, bool RES>
 __global__ void __launch_bounds__(SC_THREADS, 1) supcon_fused_kernel(SupconParams p) {
   constexpr int TM = 16 * RM, TN = 16 * RN, WP = TM + 4;
   extern __shared__ __align__(128) unsigned char raw[];
   const int P = p.d + 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(raw);          // [0] anchors, [1],[2] contrast ring
+  const int n_tiles = (p.A + TN - 1) / TN;
+  const int b_rows = RES ? n_tiles * TN : 2 * TN;             // contrast rows held in shared memory
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw);          // [0] anchors, [1],[2] contrast ring / resident set
   float* sA = reinterpret_cast<float*>(raw + 128);
-  float* sB = sA + (size_t)TM * P;                            // [2][TN][P]
-  float* sWt = sB + (size_t)2 * TN * P;                       // [TN][WP]
-  long long* sLab = reinterpret_cast<long long*>(sWt + (size_t)TN * WP);   // [2][TN]
-  float* sLse = reinterpret_cast<float*>(sLab + 2 * TN);      // [2][TN]
-  float* sNp = sLse + 2 * TN;                                 // [2][TN]
-  float* sRow = sNp + 2 * TN;                                 // [TM] per-anchor loss terms
+  float* sB = sA + (size_t)TM * P;                            // [b_rows][P]
+  float* sWt = sB + (size_t)b_rows * P;                       // [TN][WP]
+  long long* sLab = reinterpret_cast<long long*>(sWt + (size_t)TN * WP);   // [b_rows]
+  float* sLse = reinterpret_cast<float*>(sLab + b_rows);      // [b_rows]
+  float* sInvNp = sLse + b_rows;                              // [b_rows]  1 / |P(j)|
+  float* sRow = sInvNp + b_rows;                              // [TM] per-anchor loss terms
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ty = tid >> 4, tx = tid & 15;
-  const int n_tiles = (p.A + TN - 1) / TN;
   const float invA = 1.f / (float)p.A;
+  const float inv_T = 1.f / p.T;
 
   // zero the staging buffers once: rows past A are never written by a copy and must stay finite
-  for (int idx = tid; idx < (TM + 2 * TN) * P; idx += SC_THREADS) sA[idx] = 0.f;
+  for (int idx = tid; idx < (TM + b_rows) * P; idx += SC_THREADS) sA[idx] = 0.f;
   if (tid == 0) {
     umma::mbar_init(&bars[0], 1);
     umma::mbar_init(&bars[1], 1);
@@ -306,19 +311,31 @@ __global__ void __launch_bounds__(SC_THREADS, 1) supcon_fused_kernel(SupconParam
   __syncthreads();
   uint32_t a_phase = 0, b_count = 0;      // b_count: contrast tiles consumed so far (ring slot = count & 1)
 
+  if (RES) {
+    if (warp == 0) stage_rows(p, 0, p.A, sB, P, &bars[1], lane);        // every contrast row, one barrier
+    for (int j = tid; j < b_rows; j += SC_THREADS) sLab[j] = (j < p.A) ? p.labels[j % p.B] : 0;
+  }
+
   for (int phase = 0; phase < 2; ++phase) {
     if (phase == 1) {
       if (!p.dfeats) break;
       grid_arrive_wait(p.counter, gridDim.x);
+      if (RES) {
+        for (int j = tid; j < b_rows; j += SC_THREADS) {
+          sLse[j] = (j < p.A) ? __ldcg(p.lse + j) : 0.f;
+          sInvNp[j] = (j < p.A) ? 1.f / __ldcg(p.npos + j) : 1.f;
+        }
+        __syncthreads();
+      }
     }
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
       const int i0 = unit * TM;
       if (warp == 0) {
         stage_rows(p, i0, TM, sA, P, &bars[0], lane);
-        stage_rows(p, 0, TN, sB + (size_t)(b_count & 1) * TN * P, P, &bars[1 + (b_count & 1)], lane);
+        if (!RES) stage_rows(p, 0, TN, sB + (size_t)(b_count & 1) * TN * P, P, &bars[1 + (b_count & 1)], lane);
       }
       long long yi[RM];
-      float lse_i[RM], np_i[RM];
+      float lse_i[RM], inv_np_i[RM];
       int gi[RM];
 #pragma unroll
       for (int r = 0; r < RM; ++r) {
@@ -326,7 +343,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) supcon_fused_kernel(SupconParam
         const bool v = gi[r] < p.A;
         yi[r] = v ? p.labels[gi[r] % p.B] : 0;
         lse_i[r] = (phase == 1 && v) ? __ldcg(p.lse + gi[r]) : 0.f;
-        np_i[r] = (phase == 1 && v) ? __ldcg(p.npos + gi[r]) : 1.f;
+        inv_np_i[r] = (phase == 1 && v) ? 1.f / __ldcg(p.npos + gi[r]) : 1.f;
       }
       float m[RM], z[RM], ps[RM], np[RM];
       float acc[RM][NC * 4];
@@ -338,27 +355,34 @@ __global__ void __launch_bounds__(SC_THREADS, 1) supcon_fused_kernel(SupconParam
       }
       umma::mbar_wait(&bars[0], a_phase);
       a_phase ^= 1;
+      if (RES && phase == 0) {
+        umma::mbar_wait(&bars[1], 0);
+        __syncthreads();                                     // sLab visible
+      }
 
       for (int t = 0; t < n_tiles; ++t, ++b_count) {
-        const int slot = b_count & 1;
+        const int slot = RES ? t : (int)(b_count & 1);
         const int j0 = t * TN;
-        float* sBt = sB + (size_t)slot * TN * P;
-        if (warp == 0 && t + 1 < n_tiles)
-          stage_rows(p, j0 + TN, TN, sB + (size_t)(slot ^ 1) * TN * P, P, &bars[1 + (slot ^ 1)], lane);
-        if (tid < TN) {
-          const int j = j0 + tid;
-          const bool v = j < p.A;
-          sLab[slot * TN + tid] = v ? p.labels[j % p.B] : 0;
-          if (phase == 1) {
-            sLse[slot * TN + tid] = v ? __ldcg(p.lse + j) : 0.f;
-            sNp[slot * TN + tid] = v ? __ldcg(p.npos + j) : 1.f;
+        const float* sBt = sB + (size_t)slot * TN * P;
+        const int ab = slot * TN;                            // base of this tile's per-row arrays
+        if (!RES) {
+          if (warp == 0 && t + 1 < n_tiles)
+            stage_rows(p, j0 + TN, TN, sB + (size_t)(slot ^ 1) * TN * P, P, &bars[1 + (slot ^ 1)], lane);
+          if (tid < TN) {
+            const int j = j0 + tid;
+            const bool v = j < p.A;
+            sLab[ab + tid] = v ? p.labels[j % p.B] : 0;
+            if (phase == 1) {
+              sLse[ab + tid] = v ? __ldcg(p.lse + j) : 0.f;
+              sInvNp[ab + tid] = v ? 1.f / __ldcg(p.npos + j) : 1.f;
+            }
           }
+          umma::mbar_wait(&bars[1 + slot], (b_count >> 1) & 1);
+          __syncthreads();
         }
-        umma::mbar_wait(&bars[1 + slot], (b_count >> 1) & 1);
-        __syncthreads();
 
         float l[RM][RN];
-        logit_tile<RM, RN>(sA, sBt, P, p.d, ty, tx, p.T, l);
+        logit_tile<RM, RN>(sA, sBt, P, p.d, ty, tx, inv_T, l);
 
         if (phase == 0) {
 #pragma unroll
@@ -376,7 +400,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) supcon_fused_kernel(SupconParam
               const int j = j0 + tx + 16 * c;
               if (j < p.A && j != gi[r]) {
                 z[r] += __expf(l[r][c] - m[r]);
-                if (sLab[slot * TN + tx + 16 * c] == yi[r]) {
+                if (sLab[ab + tx + 16 * c] == yi[r]) {
                   ps[r] += l[r][c];
                   np[r] += 1.f;
                 }
@@ -391,10 +415,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) supcon_fused_kernel(SupconParam
               const int jl = tx + 16 * c, j = j0 + jl;
               float w = 0.f;
               if (j < p.A && gi[r] < p.A && j != gi[r]) {
-                const float pos = (sLab[slot * TN + jl] == yi[r]) ? 1.f : 0.f;
-                const float g_ij = __expf(l[r][c] - lse_i[r]) - pos / np_i[r];
-                const float g_ji = __expf(l[r][c] - sLse[slot * TN + jl]) - pos / sNp[slot * TN + jl];
-                w = (g_ij + g_ji) * invA / p.T;
+                const bool pos = sLab[ab + jl] == yi[r];
+                // G_ij + G_ji, G_ij = exp(l_ij - lse_i) - 1[j in P(i)] / |P(i)|   (1 * (1/n) == 1/n exactly)
+                float g = __expf(l[r][c] - lse_i[r]) + __expf(l[r][c] - sLse[ab + jl]);
+                if (pos) g -= inv_np_i[r] + sInvNp[ab + jl];
+                w = g * invA * inv_T;
               }
               sWt[jl * WP + ty * RM + r] = w;
             }
@@ -422,7 +447,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) supcon_fused_kernel(SupconParam
             }
           }
         }
-        __syncthreads();            // sB[slot], sWt and the per-tile arrays are free for the next stage
+        if (!RES || phase == 1) __syncthreads();   // ring slot / sWt / per-tile arrays are free for the next stage
       }
 
       if (phase == 0) {
@@ -473,7 +498,6 @@ __global__ void __launch_bounds__(SC_THREADS, 1) supcon_fused_kernel(SupconParam
       }
     }
     if (phase == 0 && !p.dfeats) grid_arrive_wait(p.counter, gridDim.x);   // loss needs every unit's partial
-    if (phase == 0 && p.dfeats) continue;
   }
   // after the grid-wide wait every partial is visible: CTA 0 adds them in unit order
   if (blockIdx.x == 0 && tid == 0) {
@@ -483,39 +507,40 @@ __global__ void __launch_bounds__(SC_THREADS, 1) supcon_fused_kernel(SupconParam
   }
 }
 
-template <int RM, int RN, int NC>
-int launch_fused(SupconParams p, cudaStream_t stream) {
+template <int RM, int RN, int NC, bool RES>
+size_t fused_smem_bytes(int A, int d) {
   constexpr int TM = 16 * RM, TN = 16 * RN, WP = TM + 4;
-  const int P = p.d + 4;
-  const size_t smem = 128 + (size_t)(TM + 2 * TN) * P * 4 + (size_t)TN * WP * 4 + (size_t)2 * TN * 8 + (size_t)4 * TN * 4 +
-                      (size_t)TM * 4;
-  static int coresident_dev[B200OCL_MAX_DEVICES] = {};
-  int& coresident = coresident_dev[device_slot()];
-  if (coresident == 0) {
-    B200OCL_CUDA(cudaFuncSetAttribute(supcon_fused_kernel<RM, RN, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    int per_sm = 0;
-    B200OCL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, supcon_fused_kernel<RM, RN, NC>, SC_THREADS, smem));
-    if (per_sm < 1) {
-      set_error("b200ocl_supcon: fused kernel does not fit on an SM (smem %zu)", smem);
-      return B200OCL_EUNSUPPORTED;
-    }
-    coresident = sm_count();          // one CTA per SM: the grid-wide wait needs every CTA resident
+  const int P = d + 4;
+  const int b_rows = RES ? (A + TN - 1) / TN * TN : 2 * TN;
+  return 128 + (size_t)(TM + b_rows) * P * 4 + (size_t)TN * WP * 4 + (size_t)b_rows * 16 + (size_t)TM * 4;
+}
+
+template <int RM, int RN, int NC, bool RES>
+int launch_fused(SupconParams p, cudaStream_t stream) {
+  constexpr int TM = 16 * RM;
+  const size_t smem = fused_smem_bytes<RM, RN, NC, RES>(p.A, p.d);
+  static bool configured_dev[B200OCL_MAX_DEVICES] = {};
+  bool& configured = configured_dev[device_slot()];
+  if (!configured) {
+    B200OCL_CUDA(cudaFuncSetAttribute(supcon_fused_kernel<RM, RN, NC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
   }
   p.n_units = (p.A + TM - 1) / TM;
+  const int coresident = sm_count();        // one CTA per SM (launch bounds): the grid-wide wait needs every CTA resident
   const int grid = p.n_units < coresident ? p.n_units : coresident;
   B200OCL_PROF("supcon", 2.0 * 4.0 * p.A * p.d + 8.0 * p.B, stream);
-  supcon_fused_kernel<RM, RN, NC><<<grid, SC_THREADS, smem, stream>>>(p);
+  supcon_fused_kernel<RM, RN, NC, RES><<<grid, SC_THREADS, smem, stream>>>(p);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
 }
 
-template <int RM, int RN>
+template <int RM, int RN, bool RES>
 int launch_fused_nc(const SupconParams& p, cudaStream_t stream) {
   switch ((p.d + 63) / 64) {
-    case 1: return launch_fused<RM, RN, 1>(p, stream);
-    case 2: return launch_fused<RM, RN, 2>(p, stream);
-    case 3: return launch_fused<RM, RN, 3>(p, stream);
-    default: return launch_fused<RM, RN, 4>(p, stream);
+    case 1: return launch_fused<RM, RN, 1, RES>(p, stream);
+    case 2: return launch_fused<RM, RN, 2, RES>(p, stream);
+    case 3: return launch_fused<RM, RN, 3, RES>(p, stream);
+    default: return launch_fused<RM, RN, 4, RES>(p, stream);
   }
 }
 
@@ -569,9 +594,10 @@ int b200ocl_supcon(const float* feats, const int64_t* labels, int B, int V, int 
   if (d % 4 == 0 && d <= SCF_MAX_D && (reinterpret_cast<uintptr_t>(feats) & 15) == 0 &&
       (!dfeats || (reinterpret_cast<uintptr_t>(dfeats) & 15) == 0)) {
     const int sms = sm_count();
-    if (p.A <= 16 * sms) return launch_fused_nc<1, 2>(p, stream);
-    if (p.A <= 32 * sms) return launch_fused_nc<2, 4>(p, stream);
-    return launch_fused_nc<4, 4>(p, stream);
+    if (p.A <= 16 * sms && fused_smem_bytes<1, 4, 4, true>(p.A, d) <= 200 * 1024) return launch_fused_nc<1, 4, true>(p, stream);
+    if (p.A <= 16 * sms) return launch_fused_nc<1, 2, false>(p, stream);
+    if (p.A <= 32 * sms) return launch_fused_nc<2, 4, false>(p, stream);
+    return launch_fused_nc<4, 4, false>(p, stream);
   }
   static bool configured_dev[B200OCL_MAX_DEVICES] = {};
   bool& configured = configured_dev[b200ocl::device_slot()];

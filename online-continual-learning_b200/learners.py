@@ -174,6 +174,7 @@ class ContinualLearner(torch.nn.Module):
         engine (one batched pass instead of one image at a time, base.py:125-134); the remaining
         small tensor algebra is torch.  error_analysis is not implemented."""
         eng = self.engine
+        eng.pack()
         acc_array = np.zeros(len(test_loaders))
         ncm = self._ncm()
         if ncm:
@@ -259,6 +260,7 @@ class ExperienceReplay(ContinualLearner):
 
     def train_learner(self, x_train, y_train):
         self.before_train(x_train, y_train)
+        self.engine.pack()          # the caller may have written the Parameters (load_state_dict, weight surgery)
         self.model = self.model.train()
         meters = {k: AverageMeter() for k in ('losses_batch', 'losses_mem', 'acc_batch', 'acc_mem')}
         for ep in range(self.epoch):
@@ -308,6 +310,7 @@ class SupContrastReplay(ContinualLearner):
 
     def train_learner(self, x_train, y_train):
         self.before_train(x_train, y_train)
+        self.engine.pack()          # the caller may have written the Parameters (load_state_dict, weight surgery)
         self.model = self.model.train()
         meters = {'losses': AverageMeter()}
         for ep in range(self.epoch):

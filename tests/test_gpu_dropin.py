@@ -1,11 +1,23 @@
 """The drop-in path itself (VERDICT r01 "what's missing" 1-2): exactly what
 experiment/run.py:38-50 does -- the REFERENCE's setup_architecture + setup_opt build an nn.Module and a
 torch.optim.SGD, `b200ocl.install()` swaps the replay-path entries of the reference's registries, then
-agents[...](model, opt, params).train_learner(uint8 NHWC) / .evaluate(test_loaders) run.  The same seeded
-script is first executed with the unmodified reference (baseline/_ref, on the same GPU) and the two end
-states are compared: buffer contents and the sequence of retrieved / evicted slots bit-exact (parity
-mode, no injected choices), weights / BN statistics within 1e-3 relative, at the BASELINE sizes
-(mem_size 5000, CIFAR-100 shapes, lr 0.1; MIR at 84x84 mem 10000)."""
+agents[...](model, opt, params).train_learner(uint8 NHWC) / .evaluate(test_loaders) run, at the BASELINE
+sizes (mem_size 5000, CIFAR-100 shapes, lr 0.1; MIR at 84x84 with mem 10000).
+
+The same seeded script is first executed with the unmodified reference (baseline/_ref, same GPU) and
+recorded after every train_learner call (one replay step per call).  The b200ocl run (parity mode: no
+injected sampler choices) must then reproduce, call by call:
+  * bit-exact: buffer_label, buffer_img, current_index, n_seen_so_far (= the slots retrieved / evicted),
+    and the states of the CPU, numpy and CUDA generators (every random decision consumed the same draws);
+  * the weight UPDATE of the step, w_after - w_before, within 1e-3 relative per tensor (north_star:
+    gradients within 1e-3 in fp32), BN running statistics within 1e-4;
+  * evaluate() accuracies.
+The reference at lr 0.1 / batch 10 is chaotic: a 1e-7 relative perturbation of its OWN initial weights moves
+conv1.weight by 3e-4 after one step and by 0.3 after eight (measured on the reference alone).  So the weights
+are compared per step from a common state: after each call the b200ocl model is loaded with the reference's
+recorded state_dict through the adopted module's own load_state_dict -- which also proves that Parameters
+and BN buffers written by the caller reach the engine."""
+import json
 import os
 import random
 import sys
@@ -22,15 +34,31 @@ import ref_harness  # noqa: E402
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(ref_harness.locate() is None, reason='baseline/_ref missing (python baseline/fetch_ref.py)')]
 
-TIMES = {}
+REPORT = {}
 
 
 def _seed(seed):
     np.random.seed(seed); random.seed(seed); torch.manual_seed(seed); torch.cuda.manual_seed(seed)
 
 
-def _script(kind, ours, steps, tasks=2, n_label=100, seed=0, **over):
-    """One seeded run of the run.py call pattern; returns the observable end state."""
+def _rng_states():
+    return (torch.get_rng_state().clone(), np.random.get_state()[1].copy(), int(np.random.get_state()[2]),
+            torch.cuda.get_rng_state().clone())
+
+
+def _same_rng(a, b):
+    return torch.equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and torch.equal(a[3], b[3])
+
+
+def _snapshot(agent):
+    return {'state': {k: v.detach().clone() for k, v in agent.model.state_dict().items()},
+            'label': agent.buffer.buffer_label.clone(), 'img': agent.buffer.buffer_img.clone(),
+            'n_seen': agent.buffer.n_seen_so_far, 'index': agent.buffer.current_index, 'rng': _rng_states()}
+
+
+def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, **over):
+    """One seeded run of the run.py call pattern, one replay step per train_learner call.
+    Reference run: returns the recorded trace.  b200ocl run: compares against `trace` call by call."""
     ref_harness.import_reference()
     from b200ocl import memory, registry
     from b200ocl.augment import Identity
@@ -46,39 +74,80 @@ def _script(kind, ours, steps, tasks=2, n_label=100, seed=0, **over):
     if ours:
         memory.set_mode(True)
         registry.install()
+    out, worst = [], {'update': 0.0, 'bn': 0.0, 'where': None}
+    t_train = t_eval = 0.0
     try:
         agent = ref_harness.build_agent(params)           # reference model + torch.optim.SGD
         if ours:
             assert type(agent).__module__.startswith('b200ocl'), 'install() did not take'
+            assert isinstance(agent.opt, torch.optim.SGD)
+            assert all(a is b for a, b in zip(agent.opt.param_groups[0]['params'], agent.model.parameters()))
             if hasattr(agent, 'transform'):
                 agent.transform = Identity()              # the reference side runs the identity kornia stub
         mem = params.mem_size
         x = torch.from_numpy(rs.rand(mem, 3, hw, hw).astype(np.float32)).cuda()
         y = torch.from_numpy(rs.randint(0, n_label, mem).astype(np.int64)).cuda()
         agent.buffer.update(x, y)                         # fill phase through the plugin
-        accs, dt_train, dt_eval = [], 0.0, 0.0
-        for t in range(tasks):
-            xt = rs.randint(0, 256, (params.batch * steps + 3, hw, hw, 3)).astype(np.uint8)   # +3: drop_last path
-            # every label occurs in the first task when n_label is small: the reference's NCM evaluate indexes a
+        before = {k: v.detach().clone() for k, v in agent.model.state_dict().items()}
+        for c in range(n_calls):
+            n = params.batch + 3                          # one step; the 3 extra samples exercise drop_last
+            xt = rs.randint(0, 256, (n, hw, hw, 3)).astype(np.uint8)
+            # every label occurs in every call when n_label is small: the reference's NCM evaluate indexes a
             # dict keyed by the labels seen in training with every buffer label (base.py:124-126)
-            yt = rs.permutation(np.arange(params.batch * steps + 3) % n_label).astype(np.int64)
+            yt = rs.permutation(np.arange(n) % n_label).astype(np.int64)
             torch.cuda.synchronize(); t0 = time.perf_counter()
             agent.train_learner(xt, yt)
-            torch.cuda.synchronize(); dt_train += time.perf_counter() - t0
-            tests = [(rs.randint(0, 256, (96, hw, hw, 3)).astype(np.uint8), rs.randint(0, n_label, 96).astype(np.int64))
-                     for _ in range(2)]
-            loaders = setup_test_loader(tests, params)
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            accs.append(np.asarray(agent.evaluate(loaders)))
-            torch.cuda.synchronize(); dt_eval += time.perf_counter() - t0
-        state = {k: v.detach().cpu().clone() for k, v in agent.model.state_dict().items()}
-        out = {'state': state, 'label': agent.buffer.buffer_label.cpu().clone(), 'img': agent.buffer.buffer_img.cpu().clone(),
-               'n_seen': agent.buffer.n_seen_so_far, 'index': agent.buffer.current_index, 'acc': np.stack(accs),
-               'lr': agent.opt.param_groups[0]['lr'], 'old_labels': list(agent.old_labels),
-               'opt_is_sgd': isinstance(agent.opt, torch.optim.SGD),
-               'opt_sees_model': all(a is b for a, b in zip(agent.opt.param_groups[0]['params'], agent.model.parameters())),
-               'rng_tail': (float(torch.rand(1)), float(np.random.rand()), float(torch.rand(1, device='cuda')))}
-        TIMES[(kind, 'b200ocl' if ours else 'reference')] = {'train_s': dt_train, 'eval_s': dt_eval, 'steps': steps * tasks}
+            torch.cuda.synchronize(); t_train += time.perf_counter() - t0
+            snap = _snapshot(agent)
+            if c in (n_calls // 2 - 1, n_calls - 1):
+                tests = [(rs.randint(0, 256, (96, hw, hw, 3)).astype(np.uint8), rs.permutation(np.arange(96) % n_label).astype(np.int64))
+                         for _ in range(2)]
+                loaders = setup_test_loader(tests, params)
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                snap['acc'] = np.asarray(agent.evaluate(loaders))
+                torch.cuda.synchronize(); t_eval += time.perf_counter() - t0
+                snap['rng_after_eval'] = _rng_states()
+            if not ours:
+                out.append(snap)
+                continue
+            ref = trace[c]
+            tag = '%s call %d' % (kind, c)
+            assert snap['n_seen'] == ref['n_seen'] and snap['index'] == ref['index'], tag
+            assert _same_rng(snap['rng'], ref['rng']), tag + ': a random decision consumed different draws'
+            assert torch.equal(snap['label'], ref['label']), tag + ': different slots evicted'
+            assert torch.equal(snap['img'], ref['img']), tag + ': different rows written'
+            for k, v in ref['state'].items():
+                w = snap['state'][k]
+                if not v.dtype.is_floating_point:
+                    assert torch.equal(v, w), (tag, k)
+                    continue
+                if 'running_' in k:
+                    err = float((v.double() - w.double()).norm() / max(float(v.double().norm()), 1e-12))
+                    if err > worst['bn']:
+                        worst['bn'] = err
+                    assert err <= 1e-4, (tag, k, err)
+                    continue
+                d_ref = v.double() - before[k].double()
+                d_own = w.double() - before[k].double()
+                den = float(d_ref.norm())
+                if den <= 1e-9 * max(float(v.double().norm()), 1e-30):
+                    assert float(d_own.norm()) <= 1e-6 * max(float(v.double().norm()), 1e-30) + 1e-12, (tag, k)   # untouched tensor
+                    continue
+                err = float((d_own - d_ref).norm() / den)
+                if err > worst['update']:
+                    worst['update'], worst['where'] = err, '%s %s' % (tag, k)
+                assert err <= 1e-3, (tag, k, err)
+            if 'acc' in ref:
+                assert np.abs(ref['acc'] - snap['acc']).max() <= 1.5 / 96, (tag, ref['acc'], snap['acc'])
+                assert _same_rng(snap['rng_after_eval'], ref['rng_after_eval']), tag + ': evaluate consumed different draws'
+            # continue from the reference's state: written through the adopted module, picked up by the engine
+            agent.model.load_state_dict(ref['state'])
+            before = {k: v.clone() for k, v in ref['state'].items()}
+        if not ours:
+            out_before = before
+        REPORT['%s/%s' % (kind, 'b200ocl' if ours else 'reference')] = {'train_s': t_train, 'eval_s': t_eval, 'calls': n_calls}
+        if ours:
+            REPORT['%s/worst' % kind] = worst
         return out
     finally:
         if ours:
@@ -86,49 +155,29 @@ def _script(kind, ours, steps, tasks=2, n_label=100, seed=0, **over):
             memory.set_mode(False)
 
 
-def _compare(ref, mine, tol=1e-3, acc_slack=2.5 / 96):
-    assert mine['opt_is_sgd'] and mine['opt_sees_model'] and mine['lr'] == ref['lr']
-    assert mine['n_seen'] == ref['n_seen'] and mine['index'] == ref['index']
-    assert mine['old_labels'] == ref['old_labels']
-    # every random generator was consumed identically (same number / order of draws on CPU, numpy and CUDA)
-    assert mine['rng_tail'] == ref['rng_tail']
-    # replay memory: same slots evicted, same rows written
-    assert torch.equal(ref['label'], mine['label'])
-    assert torch.equal(ref['img'], mine['img'])
-    worst = 0.0
-    for k, v in ref['state'].items():
-        w = mine['state'][k]
-        if not v.dtype.is_floating_point:
-            assert torch.equal(v, w), k
-            continue
-        err = float((v.double() - w.double()).norm() / max(float(v.double().norm()), 1e-12))
-        worst = max(worst, err)
-        assert err <= tol, (k, err)
-    assert np.abs(ref['acc'] - mine['acc']).max() <= acc_slack, (ref['acc'], mine['acc'])
-    return worst
-
-
-def _dump_times():
-    import json
+def _dump():
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-    with open(os.path.join(ROOT, 'gpurun_out', 'dropin_times.json'), 'w') as fh:
-        json.dump({'%s/%s' % k: v for k, v in TIMES.items()}, fh, indent=1)
+    with open(os.path.join(ROOT, 'gpurun_out', 'dropin_report.json'), 'w') as fh:
+        json.dump(REPORT, fh, indent=1)
 
 
-@pytest.mark.parametrize('kind,steps,n_label,over', [
-    ('er', 4, 10, dict(data='cifar10', mem_size=500)),                     # BASELINE config 1
-    ('aser', 4, 100, dict()),                                              # config 3: mem 5000, cifar100, lr 0.1
-    ('aser', 3, 100, dict(aser_type='asv', n_smp_cls=2.0)),
-    ('scr', 3, 10, dict()),                                                # config 2 (+ NCM evaluate over 5000 slots)
-    ('scr_aser', 3, 10, dict(n_smp_cls=2.0)),                              # SCR agent with the ASER plugins
-    ('mir', 3, 100, dict(data='mini_imagenet', mem_size=10000)),           # config 4: 84x84
-])
-def test_dropin_matches_reference_run(kind, steps, n_label, over):
-    ref = _script(kind, False, steps, n_label=n_label, **over)
-    mine = _script(kind, True, steps, n_label=n_label, **over)
-    worst = _compare(ref, mine)
-    TIMES[(kind, 'worst_rel_err')] = worst
-    _dump_times()
+CASES = [
+    ('er', 6, 10, dict(data='cifar10', mem_size=500)),                     # BASELINE config 1
+    ('aser', 6, 100, dict()),                                              # config 3: mem 5000, cifar100, lr 0.1
+    ('aser', 4, 100, dict(aser_type='asv', n_smp_cls=2.0)),
+    ('scr', 4, 10, dict()),                                                # config 2 (+ NCM evaluate over 5000 slots)
+    ('scr_aser', 4, 10, dict(n_smp_cls=2.0)),                              # SCR agent with the ASER plugins
+    ('mir', 4, 100, dict(data='mini_imagenet', mem_size=10000)),           # config 4: 84x84
+]
+
+
+@pytest.mark.parametrize('kind,n_calls,n_label,over', CASES)
+def test_dropin_matches_reference_run(kind, n_calls, n_label, over):
+    try:
+        trace = _script(kind, False, n_calls, n_label=n_label, **over)
+        _script(kind, True, n_calls, n_label=n_label, trace=trace, **over)
+    finally:
+        _dump()
 
 
 def test_reference_copy_is_unmodified():
