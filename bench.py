@@ -162,6 +162,8 @@ def run_ours(args, rank, world):
     dev_y = torch.from_numpy(host_y).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
+    mids = []
+
     def step(i, from_host):
         if from_host:
             xa = host_x[2 * i].to(dev, non_blocking=True); xs = host_x[2 * i + 1].to(dev, non_blocking=True)
@@ -169,6 +171,10 @@ def run_ours(args, rank, world):
         else:
             xa, xs, ya, ys = dev_x[2 * i], dev_x[2 * i + 1], dev_y[2 * i], dev_y[2 * i + 1]
         aser.replay_step(xa, ya, host_y[2 * i])
+        if mids is not None and len(mids) < 4096:
+            m = torch.cuda.Event(enable_timing=True)
+            m.record()
+            mids.append(m)
         scr.replay_step(xs, ys, host_y[2 * i + 1])
         if from_host:
             return float(aser.last_loss), float(scr.last_loss)       # device -> host read of the step's result
@@ -190,12 +196,15 @@ def run_ours(args, rank, world):
         barrier()
         launches0 = _native.launch_count() + _eng.graph_launch_count()
         t0 = time.perf_counter()
+        del mids[:]
         for k in range(args.steps):
             flush.fill_(k & 255)                      # L2 flush between timed iterations (outside the event pair)
             ev[k][0].record()
             step(args.warmup + k, from_host)
             ev[k][1].record()
         barrier()
+        split = {'aser_ms': float(np.median([a.elapsed_time(m) for (a, _), m in zip(ev, mids)])),
+                 'scr_ms': float(np.median([m.elapsed_time(b) for (_, b), m in zip(ev, mids)]))}
         wall = time.perf_counter() - t0
         clocks = sampler.stop() if rank == 0 else None
         per_step = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=dev)
@@ -205,6 +214,7 @@ def run_ours(args, rank, world):
         steps_ms = np.sort(t[1:].cpu().numpy())
         stats = {'median_ms': float(np.median(steps_ms)), 'p10_ms': float(steps_ms[int(0.1 * (len(steps_ms) - 1))]),
                  'p90_ms': float(steps_ms[int(round(0.9 * (len(steps_ms) - 1)))]), 'max_ms': float(steps_ms[-1])}
+        stats.update(split)
         return float(t[0].item()), _native.launch_count() + _eng.graph_launch_count() - launches0, clocks, wall, stats
 
     log('rank %d: learners built' % rank)

@@ -90,6 +90,19 @@ int b200ocl_supcon(const float* feats, const int64_t* labels, int B, int V, int 
 int b200ocl_gather_rows(const void* src, const int64_t* idx, int n_rows, size_t row_bytes, void* dst, void* stream);
 int b200ocl_scatter_rows(const void* src, const int64_t* idx, int n_rows, size_t row_bytes, void* dst, void* stream);
 
+/* ---------------------------------------------------------------- evaluate() (agents/base.py:118-175)
+ * Nearest-class-mean classification on encoder features.  class_means: for each class_ids[k] the normalised mean
+ * of the normalised features of the samples with that label (base.py:121-141); counts[k] == 0 leaves means[k]
+ * untouched (the reference draws a random vector there).  classify: pred[b] = class_ids[arg-min_k ||f_b/||f_b|| -
+ * means[k]||^2] (first minimum), *n_correct += #(pred == truth) (truth / pred / n_correct nullable).
+ * linear_argmax: pred[b] = arg-max_c (feats[b] . weight[c] + bias[c]) -- the classifier branch (base.py:172-175). */
+int b200ocl_ncm_class_means(const float* feats, const int64_t* labels, int n, int d, const int64_t* class_ids, int K,
+                            float* means, int* counts, void* stream);
+int b200ocl_ncm_classify(const float* feats, int B, int d, const float* means, int K, const int64_t* class_ids,
+                         const int64_t* truth, int64_t* pred, uint64_t* n_correct, void* stream);
+int b200ocl_linear_argmax(const float* feats, int B, int d, const float* weight, const float* bias, int C,
+                          const int64_t* truth, int64_t* pred, uint64_t* n_correct, void* stream);
+
 /* Stream feeder (continuum/data_utils.py:38-54: ToTensor on every sample + DataLoader shuffle): dst[i] = image
  * src[perm[i]] converted uint8 HWC -> fp32 CHW in [0,1] with an IEEE division by 255 (bit-identical to the
  * reference's CPU ToTensor).  perm may be NULL (identity).  h*w*3 % 4 == 0. */

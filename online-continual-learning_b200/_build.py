@@ -50,7 +50,8 @@ def build(force=False, verbose=False):
             for msg in ex.map(run, jobs):
                 if verbose and msg:
                     print(msg)
-    if jobs or not os.path.exists(LIB) or force:
+    stale = os.path.exists(LIB) and any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs if os.path.exists(o))
+    if jobs or not os.path.exists(LIB) or force or stale:
         cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
         if verbose:
             print(' '.join(cmd), flush=True)

@@ -169,46 +169,47 @@ class ContinualLearner(torch.nn.Module):
 
     @torch.no_grad()
     def evaluate(self, test_loaders):
-        """Accuracy per task (agents/base.py:118-227): nearest-class-mean over buffer features for
-        SCR / ncm_trick, arg-max of the classifier otherwise.  Encoder features come from the CUDA
-        engine (one batched pass instead of one image at a time, base.py:125-134); the remaining
-        small tensor algebra is torch.  error_analysis is not implemented."""
+        """Accuracy per task (agents/base.py:118-227): nearest-class-mean over buffer features for SCR /
+        ncm_trick, arg-max of the classifier otherwise.  Encoder features come from the engine's batched
+        eval pass (the reference runs model.features once per buffered image, base.py:125-134); class
+        means, nearest-mean / arg-max and the hit count are the kernels of csrc/ncm.cu; one device -> host
+        read per test loader.  error_analysis is not implemented."""
+        if getattr(self.params, 'error_analysis', False):
+            raise NotImplementedError('error_analysis is outside the replay-path scope')
         eng = self.engine
-        eng.pack()
+        eng.pack()                  # the caller may have written the Parameters since the last step
+        self.model.eval()           # base.py:119 (the next train_learner switches back)
         acc_array = np.zeros(len(test_loaders))
         ncm = self._ncm()
         if ncm:
             n = self.buffer.current_index
-            feats = torch.cat([eng.features_eval(self.buffer.buffer_img[s:s + 512]) for s in range(0, n, 512)]) \
+            class_ids = torch.tensor(self.old_labels, dtype=torch.int64, device=self.device)
+            feats = torch.cat([eng.features_eval(self.buffer.buffer_img[s:s + 500]) for s in range(0, n, 500)]) \
                 if n else torch.zeros((0, eng.dim_in), device=self.device)
-            feats = feats / feats.norm(dim=1, keepdim=True)
-            labels = self.buffer.buffer_label[:n]
-            means = []
-            for cls in self.old_labels:
-                sel = feats[labels == cls]
-                mu = sel.mean(0) if sel.shape[0] else torch.randn(eng.dim_in, device=self.device)
-                means.append(mu / mu.norm())
-            means = torch.stack(means) if means else torch.zeros((0, eng.dim_in), device=self.device)
-            old = torch.tensor(self.old_labels, device=self.device)
+            if n and not bool(torch.isin(self.buffer.buffer_label[:n], class_ids).all()):
+                raise KeyError('a buffered label was never seen in training (the reference raises here, base.py:126)')
+            means, counts = ops.ncm_class_means(feats, self.buffer.buffer_label[:n], class_ids)
+            empty = (counts == 0).nonzero().flatten().tolist()
+            for k in empty:         # base.py:135-137: a random direction for a class without exemplars
+                mu = torch.normal(0, 1, size=(1, eng.dim_in)).to(self.device).squeeze()
+                means[k] = mu / mu.norm()
         else:
-            names = [n for n in ('linear__weight', 'linear__bias')]
             if isinstance(self.model, EngineModel):
-                W, b = getattr(self.model, names[0]), getattr(self.model, names[1])
+                W, b = self.model.linear__weight, self.model.linear__bias
             else:
                 W, b = self.model.linear.weight, self.model.linear.bias
         for task, loader in enumerate(test_loaders):
-            correct = total = 0
+            hits = torch.zeros(1, dtype=torch.int64, device=self.device)
+            total = 0
             for batch_x, batch_y in loader:
                 batch_x, batch_y = batch_x.to(self.device), batch_y.to(self.device)
                 f = eng.features_eval(batch_x)
                 if ncm:
-                    f = f / f.norm(dim=1, keepdim=True)
-                    pred = old[torch.cdist(f, means).argmin(1)]
+                    ops.ncm_classify(f, means, class_ids, truth=batch_y, n_correct=hits)
                 else:
-                    pred = (f @ W.t() + b).argmax(1)
-                correct += int((pred == batch_y).sum())
+                    ops.linear_argmax(f, W, b, truth=batch_y, n_correct=hits)
                 total += batch_y.numel()
-            acc_array[task] = correct / max(total, 1)
+            acc_array[task] = int(hits) / max(total, 1)
         print(acc_array)
         return acc_array
 

@@ -151,6 +151,47 @@ def stream_prepare(x_u8_nhwc, perm=None):
     return out
 
 
+def ncm_class_means(feats, labels, class_ids):
+    """(means [K,d], counts [K] int32): normalised class means of normalised features (agents/base.py:121-141)."""
+    _need_cuda(feats, labels, class_ids)
+    feats, labels, class_ids = _f32(feats), _i64(labels).reshape(-1), _i64(class_ids).reshape(-1)
+    n, d = feats.shape
+    K = class_ids.numel()
+    means = torch.zeros((K, d), dtype=torch.float32, device=feats.device)
+    counts = torch.zeros(K, dtype=torch.int32, device=feats.device)
+    rc = _native.lib().b200ocl_ncm_class_means(_ptr(feats), _ptr(labels), n, d, _ptr(class_ids), K, _ptr(means),
+                                               _ptr(counts), _stream())
+    _native.check(rc, 'b200ocl_ncm_class_means')
+    return means, counts
+
+
+def ncm_classify(feats, means, class_ids, truth=None, n_correct=None):
+    """Nearest normalised class mean (agents/base.py:155-170).  Returns pred [B]; adds the number of hits to
+    n_correct (uint64 tensor [1], as int64 storage) when truth is given."""
+    _need_cuda(feats, means, class_ids, truth, n_correct)
+    feats, means, class_ids = _f32(feats), _f32(means), _i64(class_ids).reshape(-1)
+    B, d = feats.shape
+    pred = torch.empty(B, dtype=torch.int64, device=feats.device)
+    truth = None if truth is None else _i64(truth).reshape(-1)
+    rc = _native.lib().b200ocl_ncm_classify(_ptr(feats), B, d, _ptr(means), means.shape[0], _ptr(class_ids), _ptr(truth),
+                                            _ptr(pred), _ptr(n_correct), _stream())
+    _native.check(rc, 'b200ocl_ncm_classify')
+    return pred
+
+
+def linear_argmax(feats, weight, bias, truth=None, n_correct=None):
+    """arg-max of feats @ weight.T + bias (agents/base.py:172-175)."""
+    _need_cuda(feats, weight, bias, truth, n_correct)
+    feats, weight, bias = _f32(feats), _f32(weight), _f32(bias)
+    B, d = feats.shape
+    pred = torch.empty(B, dtype=torch.int64, device=feats.device)
+    truth = None if truth is None else _i64(truth).reshape(-1)
+    rc = _native.lib().b200ocl_linear_argmax(_ptr(feats), B, d, _ptr(weight), _ptr(bias), weight.shape[0], _ptr(truth),
+                                             _ptr(pred), _ptr(n_correct), _stream())
+    _native.check(rc, 'b200ocl_linear_argmax')
+    return pred
+
+
 def scatter_rows(dst, idx, src):
     """dst[idx[i]] = src[i] over the first dimension (buffer_img[idx] = x)."""
     _need_cuda(dst, idx, src)
