@@ -521,13 +521,13 @@ int launch_tcp(ConvArgs a, cudaStream_t stream) {
   const size_t limit = 227 * 1024 - 4096;     // static shared memory (barriers, coefficients) comes on top
   a.tp_ps = 3; a.tp_bs = 6;
   {
-    // TMEM accumulation chains.  Eval features feed ASER's index decisions (bit-exact bar): every tap is promoted
-    // to fp32 registers separately.  Train-mode forwards and data gradients only have the 1e-3 gradient bar: the
-    // three taps of a kernel column accumulate in TMEM before one promotion (rms error 6e-7 instead of 3e-7
-    // against an fp64 convolution, tools/tcp_chain_accuracy.py).  B200OCL_TCP_CHAIN=1|3 forces one policy.
+    // TMEM accumulation chains: every tap is promoted to fp32 registers separately (default).  Chaining the three
+    // taps of a kernel column in TMEM (B200OCL_TCP_CHAIN=3) was measured again in round 2, for the train-mode and
+    // data-gradient launches only: no change of the step time (the kernel is bound by shared-memory bandwidth --
+    // three SS-mode MMAs re-read the 4 KB A window per 8 channels for N = 32..48 columns -- not by the number of
+    // promotions) while the BN-weight gradient of layer2.0 moved from 2e-4 to 1.9e-3 off the reference: not taken.
     const char* e = getenv("B200OCL_TCP_CHAIN");
-    if (e && (e[0] == '1' || e[0] == '3')) a.tp_chain = e[0] - '0';
-    else a.tp_chain = (a.mode == CONV_EVAL) ? 1 : 3;
+    a.tp_chain = (e && e[0] == '3') ? 3 : 1;
   }
   if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) a.tp_bs = 4;
   if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) { a.tp_ps = 2; a.tp_bs = 6; }

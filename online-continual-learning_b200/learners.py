@@ -96,8 +96,7 @@ class ContinualLearner(torch.nn.Module):
         self.lbl_inv_map = {}
         self.class_task_map = {}
         trick = getattr(params, 'trick', None) or {}
-        unsupported = [k for k in ('labels_trick', 'kd_trick', 'separated_softmax', 'review_trick', 'kd_trick_star')
-                       if trick.get(k)]
+        unsupported = [k for k in ('labels_trick', 'kd_trick', 'separated_softmax', 'kd_trick_star') if trick.get(k)]
         if unsupported:
             raise NotImplementedError('tricks %s are outside the replay-path scope (SURVEY section 8f)' % unsupported)
         if isinstance(model, EngineModel):
@@ -156,6 +155,45 @@ class ContinualLearner(torch.nn.Module):
         self.new_labels_zombie = list(self.new_labels)
         self.new_labels.clear()
         self.task_seen += 1
+        if (getattr(self.params, 'trick', None) or {}).get('review_trick') and hasattr(self, 'buffer'):
+            self._review()
+
+    def _review(self):
+        """Review trick (agents/base.py:62-88, the published SCR setting config_CVPR/agent/scr/scr_5k.yml:10): one
+        pass over the filled memory in shuffled batches of eps_mem_batch (drop_last), gradients divided by 10.
+        g/10 followed by SGD(lr, wd) is p -= lr*(g/10 + wd*p) = SGD(lr/10, 10*wd) on g: folded into the step."""
+        eng = self.engine
+        lr, wd = self._lr_wd()
+        n = self.buffer.current_index
+        bs = self.params.eps_mem_batch
+        if n == 0 or n < bs:
+            return
+        self.model.train()
+        if memory.parity():
+            from torch.utils.data import DataLoader, TensorDataset
+            batches = [b[0] for b in DataLoader(TensorDataset(torch.arange(n)), batch_size=bs, shuffle=True, num_workers=0,
+                                                drop_last=True)]
+        else:
+            perm = torch.randperm(n)
+            batches = [perm[i * bs:(i + 1) * bs] for i in range(n // bs)]
+        scr = self.params.agent == 'SCR'
+        for idx in batches:
+            idx_t = memory.to_device_i64(idx.numpy(), self.device)
+            bx = ops.gather_rows(self.buffer.buffer_img, idx_t)
+            by = ops.gather_rows(self.buffer.buffer_label, idx_t)
+            out, ws = eng.forward_train(bx, slot=0)                                  # base.py:76 (for SCR: BN side effect only)
+            if scr:
+                f1, ws1 = eng.forward_train(bx, slot=0)                              # base.py:78-79
+                aug = self.transform(bx)
+                f2, ws2 = eng.forward_train(aug, slot=1)
+                loss, dfeat = ops.supcon(torch.stack((f1, f2), dim=1), by, self.params.temp)
+                eng.backward(bx, dfeat[:, 0].contiguous(), ws1)
+                eng.backward(aug, dfeat[:, 1].contiguous(), ws2, accumulate=True)
+            else:
+                ce = ce_loss(out, by, want_grad=True)
+                eng.backward(bx, ce['dlogits'], ws)
+            self._optimizer_step(lr / 10.0, wd * 10.0)                               # base.py:83-87
+            self._throttle()
 
     def train_learner(self, x_train, y_train):
         raise NotImplementedError

@@ -143,6 +143,7 @@ class ASER_update(object):
         eval_y = to_device_i64(np.concatenate([buffer.labels_host[eval_ind], cur_y_host[minority]]), dev)
         sv_sum = ops.knn_sv(eval_f, eval_y, cand_f, cand_y, self.k, want_sum=True)['sum']
         order = ops.rank_desc(sv_sum)                                  # full descending ranking
+        self.last_sv_sum = sv_sum                                      # kept for inspection (tests: tie analysis)
         buffer.n_seen_so_far += n_cur
         # The replacement itself (aser_update.py:88-112) happens on the device; the host mirror (labels,
         # class caches) follows from an asynchronous copy of the decision, applied the next time host-side

@@ -95,6 +95,7 @@ def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, noise=None, me
         x = torch.from_numpy(rs.rand(mem, 3, hw, hw).astype(np.float32)).cuda()
         y = torch.from_numpy(rs.randint(0, n_label, mem).astype(np.int64)).cuda()
         agent.buffer.update(x, y)                         # fill phase through the plugin
+        prefill_img = agent.buffer.buffer_img.clone()
         before = {k: v.detach().clone() for k, v in agent.model.state_dict().items()}
         for c in range(n_calls):
             n = params.batch + 3                          # one step; the 3 extra samples exercise drop_last
@@ -130,8 +131,24 @@ def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, noise=None, me
             if ours:
                 assert snap['n_seen'] == ref['n_seen'] and snap['index'] == ref['index'], tag
                 assert _same_rng(snap['rng'], ref['rng']), tag + ': a random decision consumed different draws'
-                assert torch.equal(snap['label'], ref['label']), tag + ': different slots evicted'
-                assert torch.equal(snap['img'], ref['img']), tag + ': different rows written'
+                if not (torch.equal(snap['label'], ref['label']) and torch.equal(snap['img'], ref['img'])):
+                    # ASER ranks summed Shapley values, which take few distinct values: candidates at the keep / evict
+                    # boundary are often tied, and the reference breaks ties with an unstable argsort
+                    # (aser_update.py:84).  A different eviction is accepted only when it is such a tie: the slots
+                    # evicted by one run and not by the other must have equal scores (<= 1e-5) in our ranking.
+                    upd = agent.buffer.update_method
+                    assert hasattr(upd, 'last_sv_sum'), tag + ': different slots written by a non-ASER update'
+                    prev_img = trace[c - 1]['img'] if c > 0 else prefill_img
+                    ev_ref = set((ref['img'] != prev_img).flatten(1).any(1).nonzero().flatten().tolist())
+                    ev_own = set((snap['img'] != prev_img).flatten(1).any(1).nonzero().flatten().tolist())
+                    cand = upd.last_choices['upd_cand_ind'].tolist()
+                    sv = upd.last_sv_sum.cpu().numpy()
+                    diff = sorted(ev_ref ^ ev_own)
+                    assert diff and all(sl in cand for sl in diff), (tag, 'evicted slots outside the candidate draw', diff)
+                    scores = np.array([sv[cand.index(sl)] for sl in diff])
+                    assert scores.max() - scores.min() <= 1e-5 * max(1.0, float(np.abs(sv).max())), (tag, diff, scores)
+                    REPORT.setdefault('%s/ties' % kind, []).append({'call': c, 'slots': diff, 'scores': scores.tolist()})
+                    break           # the memories differ from here on: the run ends with the tie verified
             spread = {'decisions_same': bool(decisions_same)}
             for k, v in ref['state'].items():
                 w = snap['state'][k]
@@ -200,6 +217,9 @@ CASES = [
     ('scr', 4, 10, dict()),                                                # config 2 (+ NCM evaluate over 5000 slots)
     ('scr_aser', 4, 10, dict(n_smp_cls=2.0)),                              # SCR agent with the ASER plugins
     ('mir', 4, 100, dict(data='mini_imagenet', mem_size=10000)),           # config 4: 84x84
+    # review trick (agents/base.py:62-88; the published SCR setting): after_train replays the memory, gradients / 10
+    ('scr', 3, 10, dict(mem_size=200, trick=dict(ref_harness.TRICK, review_trick=True))),
+    ('er', 3, 10, dict(data='cifar10', mem_size=40, trick=dict(ref_harness.TRICK, review_trick=True))),
 ]
 
 

@@ -97,7 +97,7 @@ def test_reservoir_update_golden(b, golden_dir, monkeypatch):
     upd = b.update.Reservoir_update(params)
     for s in range(g['x'].shape[0]):
         d = g['draws'][s]
-        monkeypatch.setattr(b.update, 'reservoir_draws', lambda n, n_seen, d=d: d[d >= 0][:n])
+        monkeypatch.setattr(b.update, 'reservoir_draws', lambda n, n_seen, device=None, d=d: d[d >= 0][:n])
         ret = upd.update(buf, dev(g['x'][s]), dev(g['y'][s]), y_host=g['y'][s])
         ref = g['rets'][s]
         assert list(ret) == [int(v) for v in ref[ref >= 0]], s
