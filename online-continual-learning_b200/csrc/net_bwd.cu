@@ -39,6 +39,7 @@ struct BnBwdArgs {
   int rows_per_cta;
   double* part;  // [gridDim.x][C][2]
   unsigned int* counter;
+  unsigned int* ready;   // fused kernel: set by the finalizing CTA once coef[] is written
   float* dgamma;
   float* dbeta;
   int accumulate;
@@ -179,7 +180,183 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
   }
 }
 
+
+// One cooperative launch instead of reduce + apply: every CTA keeps the masked gradient g and the normalised
+// activation xhat of its own rows in shared memory between the two phases, so dA / z / mask are read from
+// HBM / L2 once instead of twice and a launch disappears.  The per-channel sums still meet in fp64 partials that
+// the LAST arriving CTA reduces in CTA order (same association as the two-kernel path); the others spin on a
+// ready flag.  Requires the whole grid to be co-resident: grid <= number of SMs, one CTA per SM.
+__global__ void __launch_bounds__(256, 1) bn_bwd_fused_kernel(BnBwdArgs a) {
+  extern __shared__ __align__(16) double sred[];  // [max(R, groups)][C][2] doubles, then the resident rows
+  __shared__ bool is_last;
+  const int cols = a.C / 4;
+  const int R = 256 / cols;
+  const int tid = threadIdx.x;
+  const int col = tid % cols, rl = tid / cols;
+  const bool active = rl < R;
+  const int groups = 256 / a.C > 0 ? 256 / a.C : 1;
+  const int srows = R > groups ? R : groups;
+  float4* sg = reinterpret_cast<float4*>(sred + (size_t)srows * a.C * 2);      // [rows_per_cta][cols]
+  float4* sx = sg + (size_t)a.rows_per_cta * cols;
+  const int r0 = blockIdx.x * a.rows_per_cta;
+  const int r1 = min(a.M, r0 + a.rows_per_cta);
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const float4 mu = *reinterpret_cast<const float4*>(a.mean + col * 4);
+    const float4 is = *reinterpret_cast<const float4*>(a.invstd + col * 4);
+    for (int rb = r0 + rl; rb < r1; rb += 4 * R) {
+      float4 g[4], m[4], zz[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * R;
+        const size_t i = (size_t)(r < r1 ? r : rb) * cols + col;
+        g[u] = __ldg(reinterpret_cast<const float4*>(a.dA) + i);
+        zz[u] = __ldg(reinterpret_cast<const float4*>(a.z) + i);
+        m[u] = a.amask ? __ldg(reinterpret_cast<const float4*>(a.amask) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * R;
+        if (r >= r1) break;
+        float4 gm, xh;
+        gm.x = m[u].x > 0.f ? g[u].x : 0.f;
+        gm.y = m[u].y > 0.f ? g[u].y : 0.f;
+        gm.z = m[u].z > 0.f ? g[u].z : 0.f;
+        gm.w = m[u].w > 0.f ? g[u].w : 0.f;
+        xh.x = (zz[u].x - mu.x) * is.x;
+        xh.y = (zz[u].y - mu.y) * is.y;
+        xh.z = (zz[u].z - mu.z) * is.z;
+        xh.w = (zz[u].w - mu.w) * is.w;
+        s[0] += gm.x; s[1] += gm.y; s[2] += gm.z; s[3] += gm.w;
+        q[0] = fmaf(gm.x, xh.x, q[0]);
+        q[1] = fmaf(gm.y, xh.y, q[1]);
+        q[2] = fmaf(gm.z, xh.z, q[2]);
+        q[3] = fmaf(gm.w, xh.w, q[3]);
+        sg[(size_t)(r - r0) * cols + col] = gm;
+        sx[(size_t)(r - r0) * cols + col] = xh;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sred[((size_t)rl * a.C + col * 4 + j) * 2 + 0] = (double)s[j];
+      sred[((size_t)rl * a.C + col * 4 + j) * 2 + 1] = (double)q[j];
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < a.C; c += 256) {
+    double S = 0.0, Q = 0.0;
+    for (int r = 0; r < R; ++r) {
+      S += sred[((size_t)r * a.C + c) * 2 + 0];
+      Q += sred[((size_t)r * a.C + c) * 2 + 1];
+    }
+    a.part[((size_t)blockIdx.x * a.C + c) * 2 + 0] = S;
+    a.part[((size_t)blockIdx.x * a.C + c) * 2 + 1] = Q;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    const int ch = tid % a.C, grp = tid / a.C;
+    double S = 0.0, Q = 0.0;
+    if (grp < groups) {
+      unsigned int b = grp;
+      for (; b + 7u * groups < gridDim.x; b += 8u * groups) {   // eight loads in flight, fixed association
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[u] = __ldcg(reinterpret_cast<const double2*>(a.part + ((size_t)(b + u * groups) * a.C + ch) * 2));
+        S += ((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x));
+        Q += ((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y));
+      }
+      for (; b < gridDim.x; b += groups) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(a.part + ((size_t)b * a.C + ch) * 2));
+        S += v.x;
+        Q += v.y;
+      }
+      sred[((size_t)grp * a.C + ch) * 2 + 0] = S;
+      sred[((size_t)grp * a.C + ch) * 2 + 1] = Q;
+    }
+    __syncthreads();
+    if (tid < a.C) {
+      double db = 0.0, dg = 0.0;
+      for (int g = 0; g < groups; ++g) {
+        db += sred[((size_t)g * a.C + tid) * 2 + 0];
+        dg += sred[((size_t)g * a.C + tid) * 2 + 1];
+      }
+      if (a.accumulate) {
+        a.dgamma[tid] += (float)dg;
+        a.dbeta[tid] += (float)db;
+      } else {
+        a.dgamma[tid] = (float)dg;
+        a.dbeta[tid] = (float)db;
+      }
+      a.coef[tid] = a.gamma[tid] * a.invstd[tid];
+      a.coef[a.C + tid] = (float)(db / (double)a.M);
+      a.coef[2 * a.C + tid] = (float)(dg / (double)a.M);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(a.ready, 1u);
+  } else if (tid == 0) {
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.u32 %0, [%1];\n" : "=r"(seen) : "l"(a.ready) : "memory");
+    } while (seen == 0u);
+  }
+  __syncthreads();
+  if (!active) return;
+  const float4 k1 = __ldcg(reinterpret_cast<const float4*>(a.coef) + col);
+  const float4 mb = __ldcg(reinterpret_cast<const float4*>(a.coef + a.C) + col);
+  const float4 mg = __ldcg(reinterpret_cast<const float4*>(a.coef + 2 * a.C) + col);
+  for (int r = r0 + rl; r < r1; r += R) {
+    const float4 g = sg[(size_t)(r - r0) * cols + col];
+    const float4 xh = sx[(size_t)(r - r0) * cols + col];
+    float4 d;
+    d.x = k1.x * (g.x - mb.x - xh.x * mg.x);
+    d.y = k1.y * (g.y - mb.y - xh.y * mg.y);
+    d.z = k1.z * (g.z - mb.z - xh.z * mg.z);
+    d.w = k1.w * (g.w - mb.w - xh.w * mg.w);
+    const size_t i = (size_t)r * cols + col;
+    reinterpret_cast<float4*>(a.dz)[i] = d;
+    if (a.gout) reinterpret_cast<float4*>(a.gout)[i] = g;
+  }
+}
+
 int launch_bn_bwd(BnBwdArgs a, cudaStream_t stream) {
+  {
+    // fused path: rows split evenly over at most one CTA per SM, all of a CTA's rows resident in shared memory
+    static int use_fused = -1;
+    if (use_fused < 0) {
+      const char* e = getenv("B200OCL_BN_FUSED");
+      use_fused = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int cols = a.C / 4;
+    const int R = 256 / cols;
+    const int sms = sm_count();
+    int rows = (a.M + sms - 1) / sms;
+    if (rows < 4 * R) rows = 4 * R;
+    rows = (rows + R - 1) / R * R;
+    const int grid = (a.M + rows - 1) / rows;
+    const int groups = 256 / a.C > 0 ? 256 / a.C : 1;
+    const int srows = R > groups ? R : groups;
+    const size_t smem = (size_t)srows * a.C * 2 * sizeof(double) + (size_t)rows * a.C * 2 * sizeof(float);
+    if (use_fused && a.ready && grid <= sms && smem <= 200 * 1024 &&
+        (size_t)grid * a.C * 2 * sizeof(double) <= (size_t)bn_bwd_part_capacity(a.M, a.C, sms)) {
+      static bool configured_dev[B200OCL_MAX_DEVICES] = {};
+      bool& configured = configured_dev[device_slot()];
+      if (!configured) {
+        B200OCL_CUDA(cudaFuncSetAttribute(bn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+      }
+      a.rows_per_cta = rows;
+      B200OCL_PROF("bn_bwd", (a.amask ? 16.0 : 12.0) * a.M * a.C + (a.gout ? 4.0 * a.M * a.C : 0.0), stream);
+      bn_bwd_fused_kernel<<<grid, 256, smem, stream>>>(a);
+      B200OCL_LAUNCHED();
+      return B200OCL_OK;
+    }
+  }
   const int cols = a.C / 4;
   const int R = 256 / cols;
   const int rows = bn_bwd_rows_per_cta(a.M, a.C, sm_count());
@@ -647,6 +824,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     a.C = c.cout;
     a.part = bn_part;
     a.counter = counters + ci;
+    a.ready = counters + 4 * NET_MAX_CONV + ci;
     a.dgamma = st->grads + b.g_off;
     a.dbeta = st->grads + b.b_off;
     a.accumulate = accumulate;

@@ -74,6 +74,11 @@ inline int bn_bwd_rows_per_cta(int M, int C, int sms) {
   if (rows < 4 * R) rows = 4 * R;
   return (rows + R - 1) / R * R;
 }
+// bytes of BN-backward partials the workspace holds for a layer (the fused kernel's grid must fit as well)
+inline size_t bn_bwd_part_capacity(int M, int C, int sms) {
+  const int rows = bn_bwd_rows_per_cta(M, C, sms);
+  return (size_t)((M + rows - 1) / rows) * C * 2 * sizeof(double);
+}
 constexpr int NET_COEF_DOUBLES = 512;  // 3 x 160 floats of BN-backward coefficients fit in front of the partials
 
 struct TrainWs {

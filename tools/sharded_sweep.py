@@ -23,7 +23,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    E, C, d, k = 50000, 1000, 512, 3
+    E = int(os.environ.get('SWEEP_ROWS', 50000))
+    C, d, k = int(os.environ.get('SWEEP_CAND', 1000)), int(os.environ.get('SWEEP_DIM', 512)), 3
     g = torch.Generator(device='cuda').manual_seed(0)          # same data on every rank
     ef = torch.relu(torch.randn(E, d, device='cuda', generator=g))
     cf = torch.relu(torch.randn(C, d, device='cuda', generator=g))
