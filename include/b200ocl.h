@@ -35,7 +35,8 @@ extern "C" {
 #define B200OCL_EWORKSPACE 3  /* workspace too small or misaligned               */
 #define B200OCL_ECUDA 4       /* a CUDA runtime call failed                      */
 
-#define B200OCL_KNN_MAX_CAND 1024 /* candidates per call of the fused kNN-SV kernel */
+#define B200OCL_KNN_MAX_CAND 1024 /* candidates the fused (register-sorted) kNN-SV kernel takes */
+#define B200OCL_KNN_MAX_CAND_LARGE 262144 /* beyond that: the scratch-line kernel (knn_sv_large.cu), same results */
 
 const char* b200ocl_last_error(void);
 int b200ocl_version(void);
@@ -58,7 +59,8 @@ int b200ocl_profile_get(int k, char* name, int name_len, double* ms, int* launch
  * Outputs (each nullable): sv [E,C] Shapley matrix in candidate order; col_sum /
  * col_max / col_min [C] reductions over eval rows.  Distance is the squared L2 in
  * direct-difference form; equal distances rank lowest candidate index first.
- * Reductions are deterministic (fixed-order, no float atomics).  C <= 1024. */
+ * Reductions are deterministic (fixed-order, no float atomics).  C <= 262144 (one fused launch up to 1024
+ * candidates, the scratch-line kernel beyond; the workspace query covers both). */
 size_t b200ocl_knn_sv_workspace_bytes(int E, int C, int d);
 int b200ocl_knn_sv(const float* eval_f, const int64_t* eval_y, const float* cand_f, const int64_t* cand_y,
                    int E, int C, int d, int k,

@@ -150,85 +150,66 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
 
   if (warp >= 5 + TP_MW) {
     // =========================================================== patch loaders (128 threads)
-    // Software-pipelined: the global loads of stage pc + 1 are issued BEFORE stage pc is split and stored, so the
-    // L2 / HBM latency of a stage hides behind the conversion of the previous one instead of preceding it.
     const int lt = tid - 32 * (5 + TP_MW);
-    const int ch = lt & 7, r0 = lt >> 3;     // thread -> (patch row lt/8 + 16*i, 16-byte chunk lt%8)
-    const int nrow = G.prow;
-    const int hp = a.Hin + 2;
-    auto issue_loads = [&](int tile, int sl, float4 (&v)[TP_LD_MAX]) {
-      const int ch_valid = min(32, a.CK - sl * 32);       // real channels in this slice (multiple of 4)
-      const bool ch_real = ch * 4 < ch_valid;
-      // strip position of this thread's first row, then 16 rows further per pass (no divisions in the loop)
-      int img, yp, xp;
-      {
-        const int sp = tile * 128 + r0;
-        img = sp / G.pp;
-        const int rem = sp - img * G.pp;
-        yp = rem / G.wp;
-        xp = rem - yp * G.wp;
-      }
-#pragma unroll
-      for (int i = 0; i < TP_LD_MAX; ++i) {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int ri = r0 + 16 * i;
-        if (ch_real && ri < nrow) {
-          const int y = yp - 1, x = xp - 1;
-          if (img < a.N && (unsigned)y < (unsigned)a.Hin && (unsigned)x < (unsigned)a.Win)
-            v[i] = __ldg(reinterpret_cast<const float4*>(a.in + ((size_t)(img * a.Hin + y) * a.Win + x) * a.CK + sl * 32) + ch);
-        }
-        xp += 16;
-        while (xp >= G.wp) {
-          xp -= G.wp;
-          if (++yp == hp) {
-            yp = 0;
-            ++img;
-          }
-        }
-      }
-    };
     int pc = 0;
-    float4 v[TP_LD_MAX], vn[TP_LD_MAX];
-    int tile = blockIdx.x, sl = 0;
-    if (tile < G.tiles_m) issue_loads(tile, sl, v);
-    while (tile < G.tiles_m) {
-      int ntile = tile, nsl = sl + 1;
-      if (nsl == slices) {
-        nsl = 0;
-        ntile += gridDim.x;
-      }
-      const bool more = ntile < G.tiles_m;
-      if (more) issue_loads(ntile, nsl, vn);
-      const int ch_valid = min(32, a.CK - sl * 32);
-      const int nch = 2 * ((ch_valid + 7) / 8);            // 16-byte chunks the MMAs will read per row
-      const bool ch_live = ch < nch;                       // lanes with chunk >= nch idle
-      const int ps = pc % PS;
-      if (!umma::mbar_wait(&pempty[ps], (uint32_t)(((pc / PS) & 1) ^ 1))) s_fail = 1;
-      float* ph = reinterpret_cast<float*>(patch0 + (size_t)ps * 2 * G.pbytes);
-      float* pl = ph + G.pbytes / 4;
-      if (ch_live) {
+    for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
+      for (int sl = 0; sl < slices; ++sl, ++pc) {
+        const int ch_valid = min(32, a.CK - sl * 32);       // real channels in this slice (multiple of 4)
+        const int nch = 2 * ((ch_valid + 7) / 8);            // 16-byte chunks the MMAs will read per row
+        // thread -> (patch row lt/8 + 16*i, chunk lt%8): lanes with chunk >= nch idle
+        const int ch = lt & 7, r0 = lt >> 3;
+        const int nrow = G.prow;
+        const bool ch_live = ch < nch, ch_real = ch * 4 < ch_valid;
+        float4 v[TP_LD_MAX];
+        // strip position of this thread's first row, then 16 rows further per pass (no divisions in the loop)
+        int img, yp, xp;
+        {
+          const int sp = tile * 128 + r0;
+          img = sp / G.pp;
+          const int rem = sp - img * G.pp;
+          yp = rem / G.wp;
+          xp = rem - yp * G.wp;
+        }
+        const int hp = a.Hin + 2;
 #pragma unroll
         for (int i = 0; i < TP_LD_MAX; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int ri = r0 + 16 * i;
-          if (ri < nrow) {
-            float4 h, l;
-            umma::split_tf32(v[i].x, h.x, l.x); umma::split_tf32(v[i].y, h.y, l.y);
-            umma::split_tf32(v[i].z, h.z, l.z); umma::split_tf32(v[i].w, h.w, l.w);
-            const int off = umma::sw128_offset_f32(ri, ch);
-            *reinterpret_cast<float4*>(ph + off) = h;
-            *reinterpret_cast<float4*>(pl + off) = l;
+          if (ch_real && ri < nrow) {
+            const int y = yp - 1, x = xp - 1;
+            if (img < a.N && (unsigned)y < (unsigned)a.Hin && (unsigned)x < (unsigned)a.Win)
+              v[i] = __ldg(reinterpret_cast<const float4*>(a.in + ((size_t)(img * a.Hin + y) * a.Win + x) * a.CK + sl * 32) + ch);
+          }
+          xp += 16;
+          while (xp >= G.wp) {
+            xp -= G.wp;
+            if (++yp == hp) {
+              yp = 0;
+              ++img;
+            }
           }
         }
-      }
-      umma::fence_proxy_async_smem();
-      umma::mbar_arrive(&pfull[ps]);
-      ++pc;
-      if (more) {
+        const int ps = pc % PS;
+        if (!umma::mbar_wait(&pempty[ps], (uint32_t)(((pc / PS) & 1) ^ 1))) s_fail = 1;
+        float* ph = reinterpret_cast<float*>(patch0 + (size_t)ps * 2 * G.pbytes);
+        float* pl = ph + G.pbytes / 4;
+        if (ch_live) {
 #pragma unroll
-        for (int i = 0; i < TP_LD_MAX; ++i) v[i] = vn[i];
+          for (int i = 0; i < TP_LD_MAX; ++i) {
+            const int ri = r0 + 16 * i;
+            if (ri < nrow) {
+              float4 h, l;
+              umma::split_tf32(v[i].x, h.x, l.x); umma::split_tf32(v[i].y, h.y, l.y);
+              umma::split_tf32(v[i].z, h.z, l.z); umma::split_tf32(v[i].w, h.w, l.w);
+              const int off = umma::sw128_offset_f32(ri, ch);
+              *reinterpret_cast<float4*>(ph + off) = h;
+              *reinterpret_cast<float4*>(pl + off) = l;
+            }
+          }
+        }
+        umma::fence_proxy_async_smem();
+        umma::mbar_arrive(&pfull[ps]);
       }
-      tile = ntile;
-      sl = nsl;
     }
   } else if (warp == 4 + TP_MW) {
     // =========================================================== weight loader (one elected lane)
@@ -526,6 +507,8 @@ int launch_tcp(ConvArgs a, cudaStream_t stream) {
     // data-gradient launches only: no change of the step time (the kernel is bound by shared-memory bandwidth --
     // three SS-mode MMAs re-read the 4 KB A window per 8 channels for N = 32..48 columns -- not by the number of
     // promotions) while the BN-weight gradient of layer2.0 moved from 2e-4 to 1.9e-3 off the reference: not taken.
+    // Likewise a software-pipelined patch loader (loads of stage pc+1 issued before stage pc is converted): the
+    // class went from 4.15 to 4.3 ms per step pair -- the loaders were not the bound either -- and was reverted.
     const char* e = getenv("B200OCL_TCP_CHAIN");
     a.tp_chain = (e && e[0] == '3') ? 3 : 1;
   }

@@ -411,6 +411,12 @@ int dispatch_te(const KnnSvParams& p, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// knn_sv_large.cu
+size_t knn_large_workspace_bytes(int C);
+int launch_knn_large(const float* eval_f, const long long* eval_y, const float* cand_f, const long long* cand_y, int E, int C,
+                     int d, int k, float* sv, float* col_sum, float* col_max, float* col_min, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream);
 }  // namespace b200ocl
 
 extern "C" {
@@ -419,6 +425,7 @@ size_t b200ocl_knn_sv_workspace_bytes(int E, int C, int d) {
   (void)E;
   (void)d;
   if (C < 0) C = 0;
+  if (C > B200OCL_KNN_MAX_CAND) return b200ocl::knn_large_workspace_bytes(C);
   return 256 + b200ocl::align_up((size_t)b200ocl::knn_grid_cap() * 3 * (size_t)C * sizeof(float), 256);
 }
 
@@ -428,8 +435,8 @@ int b200ocl_knn_sv(const float* eval_f, const int64_t* eval_y, const float* cand
   using namespace b200ocl;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200OCL_CHECK_ARG(E >= 0 && C >= 0 && d >= 1 && k >= 1, "need E,C >= 0, d >= 1, k >= 1");
-  if (C > B200OCL_KNN_MAX_CAND) {
-    set_error("b200ocl_knn_sv: C=%d exceeds the fused kernel's limit of %d candidates", C, B200OCL_KNN_MAX_CAND);
+  if (C > B200OCL_KNN_MAX_CAND_LARGE) {
+    set_error("b200ocl_knn_sv: C=%d exceeds the limit of %d candidates", C, B200OCL_KNN_MAX_CAND_LARGE);
     return B200OCL_EUNSUPPORTED;
   }
   if (C == 0) return B200OCL_OK;
@@ -443,6 +450,9 @@ int b200ocl_knn_sv(const float* eval_f, const int64_t* eval_y, const float* cand
     return B200OCL_OK;
   }
   B200OCL_CHECK_ARG(eval_f && eval_y && cand_f && cand_y, "null input pointer");
+  if (C > B200OCL_KNN_MAX_CAND)      // rows too long for the register-resident sort: scratch-line path
+    return launch_knn_large(eval_f, reinterpret_cast<const long long*>(eval_y), cand_f, reinterpret_cast<const long long*>(cand_y),
+                            E, C, d, k, sv, col_sum, col_max, col_min, workspace, workspace_bytes, stream);
   const bool want_red = col_sum || col_max || col_min;
   KnnSvParams p{};
   p.eval_f = eval_f;

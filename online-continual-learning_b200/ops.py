@@ -8,7 +8,7 @@ import torch
 
 from . import _native
 
-KNN_MAX_CAND = 1024      # B200OCL_KNN_MAX_CAND (include/b200ocl.h)
+KNN_MAX_CAND = 262144    # B200OCL_KNN_MAX_CAND_LARGE (include/b200ocl.h)
 RANK_MAX = 4096          # b200ocl_rank_desc limit
 
 

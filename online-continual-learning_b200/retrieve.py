@@ -83,9 +83,9 @@ class ASER_retrieve(object):
         self.n_smp_cls = int(params.n_smp_cls)
         self.out_dim = n_classes[params.data]
         self.is_aser_upt = params.update == 'ASER'
-        if self.n_smp_cls * self.out_dim > ops.KNN_MAX_CAND:
-            raise ValueError('ASER retrieve: n_smp_cls*num_classes = %d candidates exceed the kNN-SV kernel limit %d'
-                             % (self.n_smp_cls * self.out_dim, ops.KNN_MAX_CAND))
+        if self.n_smp_cls * self.out_dim > min(ops.KNN_MAX_CAND, ops.RANK_MAX):
+            raise ValueError('ASER retrieve: n_smp_cls*num_classes = %d candidates exceed the kNN-SV / ranking kernel limit %d'
+                             % (self.n_smp_cls * self.out_dim, min(ops.KNN_MAX_CAND, ops.RANK_MAX)))
         ClassBalancedRandomSampling.reset()
 
     def retrieve(self, buffer, **kwargs):

@@ -92,9 +92,9 @@ class ASER_update(object):
         self.n_total_smp = int(params.n_smp_cls * self.out_dim)
         self.reservoir_update = Reservoir_update(params)
         self._last_decision = None
-        if self.n_total_smp + int(getattr(params, 'batch', 0)) > ops.KNN_MAX_CAND:
-            raise ValueError('ASER update: n_smp_cls*num_classes + batch = %d candidates exceed the kNN-SV kernel limit %d'
-                             % (self.n_total_smp + int(params.batch), ops.KNN_MAX_CAND))
+        if self.n_total_smp + int(getattr(params, 'batch', 0)) > min(ops.KNN_MAX_CAND, ops.RANK_MAX):
+            raise ValueError('ASER update: n_smp_cls*num_classes + batch = %d candidates exceed the kNN-SV / ranking kernel limit %d'
+                             % (self.n_total_smp + int(params.batch), min(ops.KNN_MAX_CAND, ops.RANK_MAX)))
         ClassBalancedRandomSampling.reset()
 
     def update(self, buffer, x, y, **kwargs):
