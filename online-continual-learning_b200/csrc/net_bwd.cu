@@ -756,6 +756,41 @@ int linear_backward(const LinL& l, const float* params, float* grads, const floa
 }  // namespace
 }  // namespace b200ocl
 
+// Weight gradients leave the critical path: wgrad(i) only feeds the final reduction, while the chain
+// BN-backward -> data gradient -> BN-backward ... is strictly serial and made of launches that fill a fraction of the
+// GPU (0.02-0.7 waves, profiles/r02_wgrad_ncu.md).  So wgrad(i) is launched on a side stream, forked after the
+// BN-backward that produced its dz and joined before the finalize; dz alternates between two buffers so that the next
+// BN-backward does not wait for it.  Fork / join are events, captured as parallel branches when the call is recorded
+// into a CUDA graph.  One side stream and four events per device, created on first (eager) use.
+namespace b200ocl {
+namespace {
+struct BwdAsync {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+  int state = 0;   // 0 = not tried, 1 = usable, -1 = disabled / failed
+};
+BwdAsync* bwd_async() {
+  static BwdAsync per_dev[B200OCL_MAX_DEVICES];
+  BwdAsync& a = per_dev[device_slot()];
+  if (a.state == 0) {
+    const char* e = getenv("B200OCL_WG_ASYNC");
+    a.state = -1;
+    if (!(e && e[0] == '0')) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);      // lo = least priority
+      bool ok = cudaStreamCreateWithPriority(&a.side, cudaStreamNonBlocking, lo) == cudaSuccess;
+      for (int i = 0; ok && i < 2; ++i)
+        ok = cudaEventCreateWithFlags(&a.ready[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&a.done[i], cudaEventDisableTiming) == cudaSuccess;
+      if (ok) a.state = 1;
+      else (void)cudaGetLastError();
+    }
+  }
+  return a.state == 1 ? &a : nullptr;
+}
+}  // namespace
+}  // namespace b200ocl
+
 extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x,
                                     const float* dout, int N, void* workspace, size_t workspace_bytes, int accumulate,
                                     void* stream_) {
@@ -833,7 +868,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     a.gout = gout;
     return launch_bn_bwd(a, stream);
   };
-  auto wgrad = [&](int ci, const float* x, const float* dz) -> int {
+  auto wgrad_on = [&](int ci, const float* x, const float* dz, cudaStream_t stream) -> int {
     const ConvL& c = p.conv[ci];
     const WgradCfg g = wgrad_cfg(c, N, sms);
     WgradArgs a{};
@@ -891,6 +926,39 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     return launch_conv(a, stream);
   };
 
+  // dz double buffer + fork / join (see bwd_async above)
+  BwdAsync* as = bwd_async();
+  float* dzbuf[2] = {w.g2, w.g4};
+  bool pending[2] = {false, false};
+  int cur = 0;
+  auto next_dz = [&]() -> float* {           // the buffer the next BN-backward writes: its last reader must be done
+    if (as && pending[cur]) {
+      if (cudaStreamWaitEvent(stream, as->done[cur], 0) != cudaSuccess) return nullptr;
+      pending[cur] = false;
+    }
+    return dzbuf[cur];
+  };
+  auto wgrad = [&](int ci, const float* xin, const float* dz) -> int {
+    if (!as) return wgrad_on(ci, xin, dz, stream);
+    B200OCL_CUDA(cudaEventRecord(as->ready[cur], stream));
+    B200OCL_CUDA(cudaStreamWaitEvent(as->side, as->ready[cur], 0));
+    const int rcw = wgrad_on(ci, xin, dz, as->side);
+    if (rcw) return rcw;
+    B200OCL_CUDA(cudaEventRecord(as->done[cur], as->side));
+    pending[cur] = true;
+    cur ^= 1;
+    return B200OCL_OK;
+  };
+  auto join_side = [&]() -> int {
+    for (int i = 0; i < 2; ++i)
+      if (as && pending[i]) {
+        B200OCL_CUDA(cudaStreamWaitEvent(stream, as->done[i], 0));
+        pending[i] = false;
+      }
+    return B200OCL_OK;
+  };
+  float* dz = nullptr;
+
   for (int b = 7; b >= 0; --b) {
     const BlockL& B = p.blk[b];
     const int prev = (b == 0) ? 0 : p.blk[b - 1].c2;
@@ -898,23 +966,27 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     const float* out_act = w.a + (size_t)N * p.conv[B.c2].act_off;
     const float* a1 = w.a + (size_t)N * p.conv[B.c1].act_off;
     // main branch, second conv
-    if ((rc = bn_backward(B.c2, g0, out_act, w.g2, B.sc < 0 ? g1 : nullptr))) return rc;
-    if ((rc = wgrad(B.c2, a1, w.g2))) return rc;
-    if ((rc = dgrad(B.c2, w.g2, w.g3, 0))) return rc;
+    if (!(dz = next_dz())) return B200OCL_ECUDA;
+    if ((rc = bn_backward(B.c2, g0, out_act, dz, B.sc < 0 ? g1 : nullptr))) return rc;
+    if ((rc = wgrad(B.c2, a1, dz))) return rc;
+    if ((rc = dgrad(B.c2, dz, w.g3, 0))) return rc;
     // shortcut branch
     if (B.sc >= 0) {
-      if ((rc = bn_backward(B.sc, g0, out_act, w.g2, nullptr))) return rc;
-      if ((rc = wgrad(B.sc, x_in, w.g2))) return rc;
-      if ((rc = dgrad(B.sc, w.g2, g1, 0))) return rc;
+      if (!(dz = next_dz())) return B200OCL_ECUDA;
+      if ((rc = bn_backward(B.sc, g0, out_act, dz, nullptr))) return rc;
+      if ((rc = wgrad(B.sc, x_in, dz))) return rc;
+      if ((rc = dgrad(B.sc, dz, g1, 0))) return rc;
     }
     // main branch, first conv
-    if ((rc = bn_backward(B.c1, w.g3, a1, w.g2, nullptr))) return rc;
-    if ((rc = wgrad(B.c1, x_in, w.g2))) return rc;
-    if ((rc = dgrad(B.c1, w.g2, g1, 1))) return rc;
+    if (!(dz = next_dz())) return B200OCL_ECUDA;
+    if ((rc = bn_backward(B.c1, w.g3, a1, dz, nullptr))) return rc;
+    if ((rc = wgrad(B.c1, x_in, dz))) return rc;
+    if ((rc = dgrad(B.c1, dz, g1, 1))) return rc;
     float* t = g0; g0 = g1; g1 = t;
   }
   // stem
-  if ((rc = bn_backward(0, g0, w.a + (size_t)N * p.conv[0].act_off, w.g2, nullptr))) return rc;
+  if (!(dz = next_dz())) return B200OCL_ECUDA;
+  if ((rc = bn_backward(0, g0, w.a + (size_t)N * p.conv[0].act_off, dz, nullptr))) return rc;
   {
     const int M = N * p.in_h * p.in_w;
     int ctas = (M + SW_PX - 1) / SW_PX;
@@ -922,8 +994,9 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     const int ppc = ((M + ctas - 1) / ctas + SW_PX - 1) / SW_PX * SW_PX;
     const int grid = (M + ppc - 1) / ppc;
     B200OCL_PROF("wgrad", 2.0 * M * 540.0, stream);
-    stem_wgrad_kernel<<<grid, 256, 0, stream>>>(x, w.g2, w.wg_part + w.wg_off[0], N, p.in_h, p.in_w, M, ppc);
+    stem_wgrad_kernel<<<grid, 256, 0, stream>>>(x, dz, w.wg_part + w.wg_off[0], N, p.in_h, p.in_w, M, ppc);
     B200OCL_LAUNCHED();
+    if ((rc = join_side())) return rc;            // every weight-gradient partial is in place
     WgFinalTable t{};
     t.n = p.n_conv;
     unsigned int blocks = 0;

@@ -94,6 +94,7 @@ struct TrainWs {
   float* g1;      // gradient w.r.t. a block input (accumulated)
   float* g2;      // dz of the current conv
   float* g3;      // gradient w.r.t. conv1's activation inside a block
+  float* g4;      // second dz buffer: weight gradients run on a side stream while the next dz is produced
   float* dfeat;
   float* dhid;
   float* dproj;
@@ -133,6 +134,7 @@ inline TrainWs train_ws(const NetPlan& p, int N, void* base, int sms) {
   w.g1 = reinterpret_cast<float*>(take(act));
   w.g2 = reinterpret_cast<float*>(take(act));
   w.g3 = reinterpret_cast<float*>(take(act));
+  w.g4 = reinterpret_cast<float*>(take(act));
   w.dfeat = reinterpret_cast<float*>(take((size_t)N * p.dim_in * sizeof(float)));
   w.dhid = reinterpret_cast<float*>(take((size_t)N * p.dim_in * sizeof(float)));
   w.dproj = reinterpret_cast<float*>(take((size_t)N * p.out_dim * sizeof(float)));
