@@ -63,7 +63,8 @@ def time_graphed(fn, reps=20, iters=10):
 def main():
     res = {}
     g = torch.Generator(device='cuda').manual_seed(0)
-    for (E, C, d) in [(10, 100, 160), (100, 100, 160), (110, 160, 160), (5000, 200, 160), (50000, 1000, 512)]:
+    for (E, C, d) in [(10, 100, 160), (100, 100, 160), (110, 160, 160), (5000, 200, 160), (50000, 1000, 512),
+                      (200, 2000, 160), (1000, 50000, 512)]:      # the last two: scratch-line kernel (C > 1024)
         ef = torch.relu(torch.randn(E, d, device='cuda', generator=g))
         cf = torch.relu(torch.randn(C, d, device='cuda', generator=g))
         ey = torch.randint(0, 100, (E,), device='cuda', generator=g)
