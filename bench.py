@@ -291,11 +291,27 @@ def profile_step(step_fn, i):
                                  '32x32): 17.3 MB per launch for 17.2 MB of input; see profiles/r01_v4_conv_tcp.md'
                                  if top == 'conv_tcp' else None),
                 'share_of_step': c['ms'] / total_ms, 'avg_launch_us': 1e3 * c['ms'] / max(c['launches'], 1)}
+        if top == 'conv_tcp':
+            # issued work: 3 TF32 passes per useful FLOP, by-product halo rows and padded channel slots (x3.4 at these shapes);
+            # the TF32 dense peak is half of the measured bf16 figure
+            roof['achieved_issued_tf32'] = achieved * 3.4
+            roof['frac_issued_vs_tf32_peak'] = achieved * 3.4 / (pk['bf16_tflops_sustained'] / 2.0)
     else:
         achieved = c['work'] / (c['ms'] * 1e-3) / 1e9 if c['ms'] > 0 else 0.0       # work = bytes
         roof = {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                 'frac': achieved / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['source'],
                 'share_of_step': c['ms'] / total_ms, 'avg_launch_us': 1e3 * c['ms'] / max(c['launches'], 1)}
+    # roofline.traffic: dram read + write bytes per launch of that class from the committed ncu pass (profiles/r02_traffic.json)
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) as fh:
+            tr = json.load(fh)
+        t = tr['classes'].get(top)
+        if t:
+            roof['traffic'] = t['dram_read_bytes_per_launch'] + t['dram_write_bytes_per_launch']
+            roof['traffic_note'] = ('dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over %d launches of this '
+                                    'class: %s' % (t['launches'], tr['command']))
+    except (OSError, ValueError, KeyError):
+        pass
     return {'roofline': roof, 'classes': {k: round(v['ms'], 4) for k, v in sorted(classes.items(), key=lambda kv: -kv[1]['ms'])}}
 
 
@@ -540,6 +556,14 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version there) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + '\n').encode())
+
     import torch
     import torch.distributed as dist
     if world > 1:
@@ -548,7 +572,7 @@ def main():
     if args.workload == 'knn_sweep':
         line = run_knn_sweep(args, rank, world)
         if rank == 0:
-            print(json.dumps(line))
+            emit(line)
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -568,7 +592,7 @@ def main():
                             'less work than in production)' % g['torch']}
                 line['vs_reference_gpu'] = {'value_ratio': line['value'] / g['stream_images_per_s'],
                                             'e2e_ratio': line['e2e']['value'] / g['stream_images_per_s']}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
