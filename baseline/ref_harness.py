@@ -96,6 +96,8 @@ def make_params(kind, **over):
         base.update(agent='ER', retrieve='random', update='random', eps_mem_batch=10)
     elif kind == 'mir':
         base.update(agent='ER', retrieve='MIR', update='random', eps_mem_batch=10)
+    elif kind == 'agem':
+        base.update(agent='AGEM', retrieve='random', update='random', eps_mem_batch=10)
     elif kind == 'scr_aser':
         base.update(agent='SCR', retrieve='ASER', update='ASER', eps_mem_batch=100)
     else:

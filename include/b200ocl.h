@@ -105,6 +105,13 @@ int b200ocl_ncm_classify(const float* feats, int B, int d, const float* means, i
 int b200ocl_linear_argmax(const float* feats, int B, int d, const float* weight, const float* bias, int C,
                           const int64_t* truth, int64_t* pred, uint64_t* n_correct, void* stream);
 
+/* A-GEM gradient projection (agents/agem.py:60-80) on flat gradient arenas: out = g - (g.g_ref / g_ref.g_ref) g_ref if
+ * g.g_ref < 0, else out = g (out may alias g_ref or g).  dots_out (nullable, [2] f32) receives g.g_ref and g_ref.g_ref.
+ * Deterministic: fp64 partials reduced in CTA order. */
+size_t b200ocl_agem_project_workspace_bytes(void);
+int b200ocl_agem_project(const float* g, const float* g_ref, float* out, size_t n, float* dots_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* Stream feeder (continuum/data_utils.py:38-54: ToTensor on every sample + DataLoader shuffle): dst[i] = image
  * src[perm[i]] converted uint8 HWC -> fp32 CHW in [0,1] with an IEEE division by 255 (bit-identical to the
  * reference's CPU ToTensor).  perm may be NULL (identity).  h*w*3 % 4 == 0. */

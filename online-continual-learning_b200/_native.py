@@ -27,6 +27,8 @@ SIGNATURES = {
     'b200ocl_ncm_class_means': (c_int, [P, P, c_int, c_int, P, c_int, P, P, P]),
     'b200ocl_ncm_classify': (c_int, [P, c_int, c_int, P, c_int, P, P, P, P, P]),
     'b200ocl_linear_argmax': (c_int, [P, c_int, c_int, P, P, c_int, P, P, P, P]),
+    'b200ocl_agem_project_workspace_bytes': (c_size_t, []),
+    'b200ocl_agem_project': (c_int, [P, P, P, c_size_t, P, P, c_size_t, P]),
     'b200ocl_sgd_step': (c_int, [P, P, P, c_size_t, c_float, c_float, P]),
     # ResNet engine: descriptor / state / info structs are passed by pointer (see engine.py)
     'b200ocl_net_query': (c_int, [P, P]),

@@ -182,6 +182,59 @@ __global__ void __launch_bounds__(256) stream_prepare_kernel(const unsigned char
     out[o] = __fdiv_rn((float)s_img[pix * 3 + c], 255.f);
   }
 }
+
+// A-GEM projection (agents/agem.py:60-80): g <- g - (g.g_ref / g_ref.g_ref) g_ref when g.g_ref < 0, else g.
+// Launch 1: per-CTA fp64 partials of the two dot products over the flat gradient arenas; launch 2: every thread
+// re-reduces the (<= 296) partials in CTA order -- same value everywhere, deterministic -- and writes the result.
+__global__ void __launch_bounds__(256) agem_dots_kernel(const float* __restrict__ g, const float* __restrict__ gref, size_t n,
+                                                        double* __restrict__ part) {
+  __shared__ double s_a[8], s_b[8];
+  double a = 0.0, b = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double x = (double)g[i], r = (double)gref[i];
+    a += x * r;
+    b += r * r;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(FULL_MASK, a, o);
+    b += __shfl_xor_sync(FULL_MASK, b, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_a[warp] = a;
+    s_b[warp] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      ta += s_a[w];
+      tb += s_b[w];
+    }
+    part[2 * blockIdx.x] = ta;
+    part[2 * blockIdx.x + 1] = tb;
+  }
+}
+
+__global__ void __launch_bounds__(256) agem_apply_kernel(const float* __restrict__ g, const float* __restrict__ gref, size_t n,
+                                                         const double* __restrict__ part, int n_part, float* __restrict__ out,
+                                                         float* __restrict__ dots_out) {
+  double prod = 0.0, prod_ref = 0.0;
+  for (int b = 0; b < n_part; ++b) {
+    prod += part[2 * b];
+    prod_ref += part[2 * b + 1];
+  }
+  const bool project = prod < 0.0;
+  const float coef = project ? (float)(prod / prod_ref) : 0.f;
+  if (dots_out && blockIdx.x == 0 && threadIdx.x == 0) {
+    dots_out[0] = (float)prod;
+    dots_out[1] = (float)prod_ref;
+  }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = project ? g[i] - coef * gref[i] : g[i];
+}
 }  // namespace
 }  // namespace b200ocl
 
@@ -239,6 +292,30 @@ int b200ocl_stream_prepare(const uint8_t* src_hwc, const int64_t* perm, int n, i
   }
   B200OCL_PROF("stream_prepare", 5.0 * n * (double)row, stream);
   stream_prepare_kernel<<<n, 256, row, stream>>>(src_hwc, reinterpret_cast<const long long*>(perm), dst_chw, h * w);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
+
+size_t b200ocl_agem_project_workspace_bytes(void) { return (size_t)2 * 2 * 148 * sizeof(double) + 256; }
+
+int b200ocl_agem_project(const float* g, const float* g_ref, float* out, size_t n, float* dots_out, void* workspace,
+                         size_t workspace_bytes, void* stream_) {
+  using namespace b200ocl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n == 0) return B200OCL_OK;
+  B200OCL_CHECK_ARG(g && g_ref && out, "null pointer");
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < b200ocl_agem_project_workspace_bytes()) {
+    set_error("b200ocl_agem_project: workspace missing, misaligned or smaller than %zu bytes", b200ocl_agem_project_workspace_bytes());
+    return B200OCL_EWORKSPACE;
+  }
+  int grid = 2 * sm_count();
+  if (grid > 296) grid = 296;
+  double* part = static_cast<double*>(workspace);
+  B200OCL_PROF("misc", 8.0 * n, stream);
+  agem_dots_kernel<<<grid, 256, 0, stream>>>(g, g_ref, n, part);
+  B200OCL_LAUNCHED();
+  B200OCL_PROF("misc", 12.0 * n, stream);
+  agem_apply_kernel<<<grid, 256, 0, stream>>>(g, g_ref, n, part, grid, out, dots_out);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
 }

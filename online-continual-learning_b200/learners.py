@@ -359,3 +359,55 @@ class SupContrastReplay(ContinualLearner):
                 if i % 100 == 1 and self.verbose:
                     print('==>>> it: {}, avg. loss: {:.6f}, '.format(i, meters['losses'].avg()))
         self.after_train()
+
+
+class AGEM(ContinualLearner):
+    """Averaged GEM (agents/agem.py:11-90) on the engine: the gradient of the stream batch is projected against the
+    gradient of a memory batch of earlier tasks when their inner product is negative -- two train-mode
+    forward / backward passes over the flat gradient arena and one projection kernel (no per-parameter Python loops)."""
+
+    def __init__(self, model, opt, params):
+        super().__init__(model, opt, params)
+        self.buffer = Buffer(model, params)
+        self.mem_size = params.mem_size
+        self.eps_mem_batch = params.eps_mem_batch
+        self.mem_iters = params.mem_iters
+        self._g_cur = torch.empty_like(self.engine.state.grads)
+
+    def replay_step(self, batch_x, batch_y, batch_y_host, meters=None):
+        """One iteration of agem.py:36-84."""
+        eng = self.engine
+        lr, wd = self._lr_wd()
+        for _ in range(self.mem_iters):
+            logits, ws = eng.forward_train(batch_x, slot=0)                          # :39
+            ce = ce_loss(logits, batch_y, want_grad=True, want_correct=meters is not None)
+            if meters is not None:
+                meters['acc_batch'].update(ce['n_correct'] / batch_y.size(0), batch_y.size(0))
+                meters['losses_batch'].update(ce['loss'], batch_y.size(0))
+            eng.backward(batch_x, ce['dlogits'], ws)                                 # :53-54
+            self.last_loss = ce['loss']
+            if self.task_seen > 0:
+                mem_x, mem_y = self.buffer.retrieve()                                # :58 (no kwargs)
+                if mem_x.size(0) > 0:
+                    self._g_cur.copy_(eng.state.grads)                               # :62 grad of the current batch
+                    mem_logits, ws_m = eng.forward_train(mem_x, slot=1)              # :65
+                    ce_m = ce_loss(mem_logits, mem_y, want_grad=True)
+                    eng.backward(mem_x, ce_m['dlogits'], ws_m)                       # :67-68 -> grad_ref in the arena
+                    ops.agem_project(self._g_cur, eng.state.grads, out=eng.state.grads)   # :73-80
+            self._optimizer_step(lr, wd)                                             # :81
+        self.buffer.update(batch_x, batch_y, y_host=batch_y_host)                    # :83
+        self._throttle()
+
+    def train_learner(self, x_train, y_train):
+        self.before_train(x_train, y_train)
+        self.engine.pack()
+        self.model = self.model.train()
+        meters = {k: AverageMeter() for k in ('losses_batch', 'acc_batch')}
+        for ep in range(self.epoch):
+            stream = StreamFeeder(x_train, y_train, self.batch, self.device)
+            for i, (batch_x, batch_y, y_host) in enumerate(stream):
+                self.replay_step(batch_x, batch_y, y_host, meters if self.verbose else None)
+                if i % 100 == 1 and self.verbose:
+                    print('==>>> it: {}, avg. loss: {:.6f}, running train acc: {:.3f}'
+                          .format(i, meters['losses_batch'].avg(), meters['acc_batch'].avg()))
+        self.after_train()

@@ -192,6 +192,22 @@ def linear_argmax(feats, weight, bias, truth=None, n_correct=None):
     return pred
 
 
+def agem_project(g, g_ref, out=None, want_dots=False):
+    """A-GEM projection of the flat gradient g against g_ref (agents/agem.py:60-80); out may alias either input."""
+    _need_cuda(g, g_ref, out)
+    g, g_ref = _f32(g).reshape(-1), _f32(g_ref).reshape(-1)
+    if g.numel() != g_ref.numel():
+        raise ValueError('g and g_ref must have the same length')
+    if out is None:
+        out = torch.empty_like(g)
+    dots = torch.empty(2, dtype=torch.float32, device=g.device) if want_dots else None
+    lib = _native.lib()
+    ws = _workspace(lib.b200ocl_agem_project_workspace_bytes(), g.device)
+    rc = lib.b200ocl_agem_project(_ptr(g), _ptr(g_ref), _ptr(out), g.numel(), _ptr(dots), _ptr(ws), ws.numel(), _stream())
+    _native.check(rc, 'b200ocl_agem_project')
+    return (out, dots) if want_dots else out
+
+
 def scatter_rows(dst, idx, src):
     """dst[idx[i]] = src[i] over the first dimension (buffer_img[idx] = x)."""
     _need_cuda(dst, idx, src)

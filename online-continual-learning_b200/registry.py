@@ -9,13 +9,14 @@ already hold), so `general_main.py` runs unchanged:
 
 Every other agent / plugin of the reference stays registered and untouched.
 """
-from .learners import ExperienceReplay, SupContrastReplay
+from .learners import AGEM, ExperienceReplay, SupContrastReplay
 from .retrieve import ASER_retrieve, MIR_retrieve, Random_retrieve
 from .update import ASER_update, Reservoir_update
 
 agents = {
     'ER': ExperienceReplay,
     'SCR': SupContrastReplay,
+    'AGEM': AGEM,
 }
 
 retrieve_methods = {

@@ -257,6 +257,7 @@ CASES = [
     ('scr', 4, 10, dict()),                                                # config 2 (+ NCM evaluate over 5000 slots)
     ('scr_aser', 4, 10, dict(n_smp_cls=2.0)),                              # SCR agent with the ASER plugins
     ('mir', 4, 100, dict(data='mini_imagenet', mem_size=10000)),           # config 4: 84x84
+    ('agem', 4, 100, dict(mem_size=1000)),                                 # A-GEM on the flat gradient arena
     # review trick (agents/base.py:62-88; the published SCR setting): after_train replays the memory, gradients / 10
     ('scr', 3, 10, dict(mem_size=200, trick=dict(ref_harness.TRICK, review_trick=True))),
     ('er', 3, 10, dict(data='cifar10', mem_size=40, trick=dict(ref_harness.TRICK, review_trick=True))),

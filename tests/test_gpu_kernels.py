@@ -268,3 +268,22 @@ def test_stream_prepare_matches_totensor(ops, n, hw):
     assert torch.equal(got, ref)
     ident = ops.stream_prepare(torch.from_numpy(x).cuda()).cpu()
     assert torch.equal(ident, torch.stack([tt(x[i]) for i in range(n)]))
+
+
+@pytest.mark.parametrize('flip', [False, True])
+def test_agem_projection(ops, flip):
+    """agents/agem.py:73-80 on flat gradient vectors: projection iff the inner product is negative."""
+    rs = np.random.RandomState(11)
+    g = rs.standard_normal(1109240).astype(np.float32)
+    r = rs.standard_normal(1109240).astype(np.float32)
+    if (np.dot(g.astype(np.float64), r.astype(np.float64)) < 0) != flip:
+        r = -r
+    out, dots = ops.agem_project(dev(g), dev(r), want_dots=True)
+    prod, prod_ref = np.dot(g.astype(np.float64), r.astype(np.float64)), np.dot(r.astype(np.float64), r.astype(np.float64))
+    ref = g - (prod / prod_ref) * r if prod < 0 else g
+    np.testing.assert_allclose(dots.cpu().numpy(), [prod, prod_ref], rtol=1e-5)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+    # in place on the reference-gradient arena, and deterministic
+    arena = dev(r).clone()
+    ops.agem_project(dev(g), arena, out=arena)
+    assert torch.equal(arena, out)
