@@ -610,9 +610,10 @@ int b200ocl_supcon(const float* feats, const int64_t* labels, int B, int V, int 
     const int sms = sm_count();
     if (p.A <= 16 * sms && fused_smem_bytes<1, 4, 4, true>(p.A, d) <= 200 * 1024) return launch_fused_nc<1, 4, true, 1>(p, stream);
     if (p.A <= 16 * sms) return launch_fused_nc<1, 2, false, 1>(p, stream);
-    // large anchor sets: 32-anchor blocks, TWO CTAs per SM (16 warps: the 64-anchor / one-CTA variant issued on 40 % of
-    // its slots with 2 warps per scheduler, profiles/r02_supcon_ncu.md); 64-anchor blocks only when d is too long for that
-    if (d <= 128 || env_flag("B200OCL_SUPCON_2CTA")) return launch_fused_nc<2, 4, false, 2>(p, stream);
+    // large anchor sets: 64-anchor blocks, one CTA per SM.  A 32-anchor / two-CTAs-per-SM variant (16 warps per SM,
+    // B200OCL_SUPCON_2CTA=1) was measured at the same 17 TFLOP/s (2.99 vs 2.90 ms at B = 4096): occupancy is not what
+    // bounds the kernel; the 4 x 4 register tile's lower shared-memory traffic per FMA is kept as the default.
+    if (d <= 128 && env_flag("B200OCL_SUPCON_2CTA")) return launch_fused_nc<2, 4, false, 2>(p, stream);
     return launch_fused_nc<4, 4, false, 1>(p, stream);
   }
   static bool configured_dev[B200OCL_MAX_DEVICES] = {};
