@@ -55,7 +55,7 @@ REPORT = {}
 # cancellation behind the first BatchNorm; 1.0e-2 of itself at batch 10) is also accepted when its error is below
 # STEP_SHARE_TOL of the whole step, and never beyond GROSS_TOL of itself.  The worst tensor of every
 # case is written to gpurun_out/dropin_report.json.
-BASE_TOL = 5e-3
+BASE_TOL = 2e-3
 VECTOR_TOL = 1.5e-3
 STEP_SHARE_TOL = 1e-3     # a tensor may also differ by up to 1e-3 of the norm of the WHOLE step
 GROSS_TOL = 5e-2          # ... but never by more than 5 % of itself (catches a wrong scale / a missing term)
