@@ -762,7 +762,7 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     return launch_conv_tc(a, stream);
   }
   if (a.force_path == 0) {
-    if (conv_tcp_eligible(a)) return launch_conv_tcp(a, stream);
+    if (conv_tcp_eligible(a) && conv_tcp_mode_allowed(a)) return launch_conv_tcp(a, stream);   // precision policy: conv_tcp.cu
     if (conv_tc_eligible(a)) return launch_conv_tc(a, stream);
   }
   // Forward convolutions and stride-1 data gradients with enough pixels go to the patch kernel:

@@ -54,10 +54,11 @@ struct ConvArgs {
 // Upper bound of gridDim.x over every tiling launch_conv may choose (sizes stat_part).
 int conv_max_grid_m(int M);
 int launch_conv(const ConvArgs& a, cudaStream_t stream);   // CK, CN multiples of 20
-int launch_stem(const ConvArgs& a, cudaStream_t stream);
+int launch_stem(const ConvArgs& a, cudaStream_t stream);   // CK == 3, CN == 20, ks == 3, NCHW input
 int launch_conv_tc(const ConvArgs& a, cudaStream_t stream);  // conv_tc.cu: tcgen05 3xTF32 path
 bool conv_tc_eligible(const ConvArgs& a);
 int launch_conv_tcp(const ConvArgs& a, cudaStream_t stream);  // conv_tcp.cu: tcgen05 fed from a halo patch
-bool conv_tcp_eligible(const ConvArgs& a);   // CK == 3, CN == 20, ks == 3, NCHW input
+bool conv_tcp_eligible(const ConvArgs& a);
+bool conv_tcp_mode_allowed(const ConvArgs& a);   // launch kinds (eval / train / data gradient) the policy sends to conv_tcp
 
 }  // namespace b200ocl

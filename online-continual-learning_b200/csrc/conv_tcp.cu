@@ -539,12 +539,7 @@ int launch_tcp(ConvArgs a, cudaStream_t stream) {
 
 }  // namespace
 
-bool conv_tcp_eligible(const ConvArgs& a) {
-  // read per call (a getenv is negligible next to a launch) so that tools can switch paths in-process
-  const char* e = getenv("B200OCL_TCP");
-  const char* e2 = getenv("B200OCL_TC");
-  const bool enabled = !((e && e[0] == '0') || (e2 && e2[0] == '0'));
-  if (!enabled || !a.w_tp || a.transposed || a.CK % 4 != 0) return false;
+bool conv_tcp_mode_allowed(const ConvArgs& a) {
   {
     // Which launch kinds take the tensor-core path: bit 0 eval features, bit 1 train-mode forward, bit 2 data gradient.
     // Default 5 = eval + data gradient.  Measured in round 2 against the live reference (tests/test_gpu_dropin.py, A-GEM
@@ -558,8 +553,16 @@ bool conv_tcp_eligible(const ConvArgs& a) {
       modes = (m && m[0] >= '0' && m[0] <= '7') ? (m[0] - '0') : 5;
     }
     const int bit = a.mode == CONV_EVAL ? 1 : (a.mode == CONV_TRAIN ? 2 : 4);
-    if (!(modes & bit)) return false;
+    return (modes & bit) != 0;
   }
+}
+
+bool conv_tcp_eligible(const ConvArgs& a) {
+  // read per call (a getenv is negligible next to a launch) so that tools can switch paths in-process
+  const char* e = getenv("B200OCL_TCP");
+  const char* e2 = getenv("B200OCL_TC");
+  const bool enabled = !((e && e[0] == '0') || (e2 && e2[0] == '0'));
+  if (!enabled || !a.w_tp || a.transposed || a.CK % 4 != 0) return false;
   if (!((a.ks == 3 && a.pad == 1) || (a.ks == 1 && a.pad == 0))) return false;
   if (a.stride != 1 && (a.stride != 2 || a.flip)) return false;          // stride 2: forward only
   if (a.Hout != (a.Hin + 2 * a.pad - a.ks) / a.stride + 1 || a.Wout != (a.Win + 2 * a.pad - a.ks) / a.stride + 1) return false;
