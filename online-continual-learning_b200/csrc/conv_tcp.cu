@@ -52,8 +52,14 @@ using umma::mbar_expect_tx;
 using umma::bulk_g2s;
 
 // acc += the NT fp32 columns of this warp's 32 TMEM lanes: all loads issued, one wait
+// comp: compensation of the TMEM accumulate's rounding.  tcgen05 kind::tf32 accumulation rounds every accumulate step
+// DOWN (toward -inf): a read-out value sits ~0.25 fp32 ulp per accumulated MMA below the exact sum, i.e. z - c|z| -- not a
+// scale factor (BatchNorm would absorb that) but a small kink at zero that a train-mode forward differentiates.  Measured
+// in round 2 (tests/test_gpu_dropin.py, A-GEM case against the live reference): without compensation conv1.weight's
+// update is 1.0e-2 off; v + comp * |v| with comp = n_mma * 2^-25 brings every tensor inside 1.1e-4 -- the same as the fp32
+// kernels (4.27e-5 vs 4.26e-5 on the whole update vector); a relative correction v * (1 + comp) changes nothing.
 template <int NT>
-__device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NT]) {
+__device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NT], float comp = 0.f) {
   uint32_t r[NT];
 #pragma unroll
   for (int c0 = 0; c0 < NT; c0 += 16) {
@@ -66,7 +72,10 @@ __device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NT]
   }
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-  for (int c = 0; c < NT; ++c) acc[c] += __uint_as_float(r[c]);
+  for (int c = 0; c < NT; ++c) {
+    const float v = __uint_as_float(r[c]);
+    acc[c] += fmaf(comp, fabsf(v), v);
+  }
 }
 
 struct TileGeom {
@@ -355,7 +364,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) conv_tcp_kernel(ConvArgs a) {
           const int t = 2 * mwq + (cq & 1);
           if (!umma::mbar_wait(&tfull[t], (uint32_t)((cq >> 1) & 1))) s_fail = 1;
           umma::fence_after_thread_sync();
-          tmem_accumulate<NT>(my_lanes + (uint32_t)(t * NT), acc);
+          {
+            // 3 MMAs per K step of this slice have accumulated into the buffer (x3 with 3-tap chains)
+            const float n_mma = 3.f * (float)((min(32, a.CK - sl * 32) + 7) / 8) * (chain3 ? 3.f : 1.f);
+            tmem_accumulate<NT>(my_lanes + (uint32_t)(t * NT), acc, a.tp_debias * n_mma * 2.9802322e-8f);   // 2^-25
+          }
           umma::fence_before_thread_sync();
           umma::mbar_arrive(&tempty[t]);
         }
@@ -511,6 +524,8 @@ int launch_tcp(ConvArgs a, cudaStream_t stream) {
     // class went from 4.15 to 4.3 ms per step pair -- the loaders were not the bound either -- and was reverted.
     const char* e = getenv("B200OCL_TCP_CHAIN");
     a.tp_chain = (e && e[0] == '3') ? 3 : 1;
+    const char* db = getenv("B200OCL_TCP_DEBIAS");      // multiplier of the rounding compensation (default 1, 0 = off)
+    a.tp_debias = db ? (float)atof(db) : 1.f;
   }
   if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) a.tp_bs = 4;
   if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) { a.tp_ps = 2; a.tp_bs = 6; }
@@ -541,16 +556,16 @@ int launch_tcp(ConvArgs a, cudaStream_t stream) {
 
 bool conv_tcp_mode_allowed(const ConvArgs& a) {
   {
-    // Which launch kinds take the tensor-core path: bit 0 eval features, bit 1 train-mode forward, bit 2 data gradient.
-    // Default 5 = eval + data gradient.  Measured in round 2 against the live reference (tests/test_gpu_dropin.py, A-GEM
-    // case, one step from torch's default initialisation): with the TRAIN-MODE FORWARD on the 3xTF32 tensor path the update
-    // of conv1.weight is 1.0e-2 off the reference (whose own one-ulp spread is 4e-6) and only 8 % of the tensors are inside
-    // 1e-3; with it on the fp32 kernels every tensor is inside 5e-5 -- eval features and data gradients on the tensor
-    // path do not matter (modes 1 and 5 give the same 5e-5).  Step pair: 8.59 ms (7) / 8.87 ms (5) / 9.26 ms (1).
+    // Which launch kinds take the tensor-core path: bit 0 eval features, bit 1 train-mode forward, bit 2 data gradient
+    // (B200OCL_TCP_MODES, default 7 = all).  The switch exists because of a round-2 finding (tests/test_gpu_dropin.py, A-GEM
+    // case against the live reference): WITHOUT the rounding compensation of tmem_accumulate() the train-mode forward on this
+    // path puts conv1.weight's update 1.0e-2 off the reference and only 8 % of the tensors inside 1e-3, while modes 1 and 5
+    // (train-mode forward on the fp32 kernels) give 5e-5.  With the compensation all three kinds are as good as fp32.
+    // Step pair: 8.59 ms (7) / 8.87 ms (5) / 9.26 ms (1).
     static int modes = -1;
     if (modes < 0) {
       const char* m = getenv("B200OCL_TCP_MODES");
-      modes = (m && m[0] >= '0' && m[0] <= '7') ? (m[0] - '0') : 5;
+      modes = (m && m[0] >= '0' && m[0] <= '7') ? (m[0] - '0') : 7;
     }
     const int bit = a.mode == CONV_EVAL ? 1 : (a.mode == CONV_TRAIN ? 2 : 4);
     return (modes & bit) != 0;

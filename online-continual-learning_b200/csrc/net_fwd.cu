@@ -433,6 +433,40 @@ int conv_eval(const NetPlan& p, const b200ocl_net_state& st, int ci, int N, cons
   return ci == 0 ? launch_stem(a, stream) : launch_conv(a, stream);
 }
 
+
+// Diagnostic (B200OCL_RESTAT=1): recompute a layer's batch mean / invstd from the STORED raw output, two passes in
+// fp64, one CTA per channel -- isolates "the statistics of the producing kernel" from "the values it stored".
+__global__ void __launch_bounds__(256) bn_restat_kernel(const float* __restrict__ z, int M, int C, float eps,
+                                                        float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  __shared__ double s_a[256];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  double s = 0.0;
+  for (int m = tid; m < M; m += 256) s += (double)z[(size_t)m * C + c];
+  s_a[tid] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) s_a[tid] += s_a[tid + o];
+    __syncthreads();
+  }
+  const double mean = s_a[0] / (double)M;
+  __syncthreads();
+  double q = 0.0;
+  for (int m = tid; m < M; m += 256) {
+    const double dlt = (double)z[(size_t)m * C + c] - mean;
+    q += dlt * dlt;
+  }
+  s_a[tid] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) s_a[tid] += s_a[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    mean_out[c] = (float)mean;
+    invstd_out[c] = (float)(1.0 / sqrt(s_a[0] / (double)M + (double)eps));
+  }
+}
+
 int conv_train(const NetPlan& p, const b200ocl_net_state& st, const TrainWs& w, int ci, int N, const float* in,
                cudaStream_t stream) {
   ConvArgs a;
@@ -446,7 +480,17 @@ int conv_train(const NetPlan& p, const b200ocl_net_state& st, const TrainWs& w, 
   a.save_invstd = w.save + b.save_off + b.c;
   a.run_mean = st.bn_stats + b.stat_off;
   a.run_var = st.bn_stats + b.stat_off + b.c;
-  return ci == 0 ? launch_stem(a, stream) : launch_conv(a, stream);
+  const int rc = ci == 0 ? launch_stem(a, stream) : launch_conv(a, stream);
+  static int restat = -1;
+  if (restat < 0) {
+    const char* e = getenv("B200OCL_RESTAT");
+    restat = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (rc == 0 && restat) {
+    bn_restat_kernel<<<c.cout, 256, 0, stream>>>(a.out, N * c.hout * c.wout, c.cout, a.eps, a.save_mean, a.save_invstd);
+    B200OCL_LAUNCHED();
+  }
+  return rc;
 }
 
 int bn_apply_train(const NetPlan& p, const b200ocl_net_state& st, const TrainWs& w, int ci, int N, int res_conv,

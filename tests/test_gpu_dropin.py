@@ -39,6 +39,7 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(ref_harness.locate() is None, reason='baseline/_ref missing (python baseline/fetch_ref.py)')]
 
 REPORT = {}
+REPORT_ONLY = bool(os.environ.get('B200OCL_DROPIN_REPORT_ONLY'))   # diagnostics: record the errors, skip the tolerance asserts
 # The update of one step is checked at two levels.  (1) The whole update vector (all 1.1 M parameters, the
 # direction the optimizer actually moves): relative error <= VECTOR_TOL = 1.5e-3, the north-star's gradient bar,
 # or SPREAD_FACTOR x the reference's own one-ulp spread of that vector where that is larger (at some states a
@@ -218,8 +219,10 @@ def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, noise=None, me
                     tol = max(BASE_TOL, SPREAD_FACTOR * sp, STEP_SHARE_TOL * step_norm / den)
                     if err / tol > worst['update'] / (worst['tolerance_there'] or 1.0):
                         worst['update'], worst['where'], worst['tolerance_there'] = err, '%s %s' % (tag, k), tol
-                    assert err <= tol, (tag, k, err, 'reference one-ulp spread', sp, 'share of the step', abs_err / step_norm)
-                    assert err <= max(GROSS_TOL, SPREAD_FACTOR * sp), (tag, k, err, 'gross per-tensor error')
+                    worst['max_err_well_conditioned'] = max(worst.get('max_err_well_conditioned', 0.0), err if sp < 1e-4 else 0.0)
+                    if not REPORT_ONLY:
+                        assert err <= tol, (tag, k, err, 'reference one-ulp spread', sp, 'share of the step', abs_err / step_norm)
+                        assert err <= max(GROSS_TOL, SPREAD_FACTOR * sp), (tag, k, err, 'gross per-tensor error')
             vec_err = (vec_num / vec_den) ** 0.5 if vec_den > 0 else 0.0
             spread['__vector__'] = vec_err
             noise_out.append(spread)
@@ -228,7 +231,8 @@ def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, noise=None, me
                 if vec_err / vec_tol >= worst.get('vector', 0.0) / worst.get('vector_tolerance', 1.0):
                     worst['vector'], worst['vector_tolerance'] = vec_err, vec_tol
                 worst['tensors_inside_1e-3'] = min(worst.get('tensors_inside_1e-3', 1.0), n_inside / max(n_tensors, 1))
-                assert vec_err <= vec_tol, (tag, 'whole update vector', vec_err, 'reference one-ulp spread', noise[c].get('__vector__'))
+                if not REPORT_ONLY:
+                    assert vec_err <= vec_tol, (tag, 'whole update vector', vec_err, 'reference one-ulp spread', noise[c].get('__vector__'))
             if ours and 'acc' in ref:
                 assert np.abs(ref['acc'] - snap['acc']).max() <= 3.1 / 96, (tag, ref['acc'], snap['acc'])   # chance-level data: <= 3 of 96 samples
                 assert _same_rng(snap['rng_after_eval'], ref['rng_after_eval']), tag + ': evaluate consumed different draws'
