@@ -26,7 +26,7 @@ struct ConvArgs {
   int tp_bn, tp_slices;
   int tp_ps, tp_bs;  // set by the launcher: patch stages, weight ring depth
   int tp_chain;      // taps accumulated in TMEM before a promotion: 1 (default) or 3 (B200OCL_TCP_CHAIN=3)
-  float tp_debias;   // multiplier of the TMEM-accumulate rounding compensation (1 = on, 0 = off; conv_tcp.cu tmem_accumulate)
+  float tp_debias;   // multiplier of the experimental TMEM-accumulate rounding compensation (default 0; conv_tcp.cu tmem_accumulate)
   int force_path;    // 0 automatic; 1 CUDA-core kernels only; 2 conv_tc; 3 conv_tcp (selftest: fails if not eligible)
   int parity_order;  // stride-2 data gradient only: pixels enumerated [parity class][n][h/2][w/2] so that a CTA
                      //    sees one class and skips the taps that cannot reach it (9 of 36 tap-pixel pairs are live)

@@ -27,9 +27,6 @@ namespace {
 
 constexpr int TC_THREADS = 128;
 constexpr int A_TILE = 128 * 32;  // floats
-// The TMEM accumulate rounds down: ~2^-25 |v| per accumulated MMA (conv_tcp.cu, tmem_accumulate).  A K block here is
-// always 4 K steps x 3 MMAs.
-constexpr float TC_ROUND_COMP = 12.f * 2.9802322e-8f;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned int s = static_cast<unsigned int>(__cvta_generic_to_shared(smem_dst));
@@ -43,7 +40,7 @@ __device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NT]
     float v[16];
     umma::tmem_ld16(taddr + (uint32_t)c0, v);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[c0 + j] += fmaf(TC_ROUND_COMP, fabsf(v[j]), v[j]);
+    for (int j = 0; j < 16; ++j) acc[c0 + j] += v[j];
   }
 }
 

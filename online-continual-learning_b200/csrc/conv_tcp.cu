@@ -52,12 +52,14 @@ using umma::mbar_expect_tx;
 using umma::bulk_g2s;
 
 // acc += the NT fp32 columns of this warp's 32 TMEM lanes: all loads issued, one wait
-// comp: compensation of the TMEM accumulate's rounding.  tcgen05 kind::tf32 accumulation rounds every accumulate step
-// DOWN (toward -inf): a read-out value sits ~0.25 fp32 ulp per accumulated MMA below the exact sum, i.e. z - c|z| -- not a
-// scale factor (BatchNorm would absorb that) but a small kink at zero that a train-mode forward differentiates.  Measured
-// in round 2 (tests/test_gpu_dropin.py, A-GEM case against the live reference): without compensation conv1.weight's
-// update is 1.0e-2 off; v + comp * |v| with comp = n_mma * 2^-25 brings every tensor inside 1.1e-4 -- the same as the fp32
-// kernels (4.27e-5 vs 4.26e-5 on the whole update vector); a relative correction v * (1 + comp) changes nothing.
+// comp: EXPERIMENTAL compensation of the TMEM accumulate's rounding (B200OCL_TCP_DEBIAS, default off).  Round-2 finding:
+// tcgen05 kind::tf32 accumulation rounds every accumulate step DOWN (toward -inf), so a read-out value is z - c|z| for a
+// small data-dependent c -- not a scale factor (a relative correction changes nothing, BatchNorm absorbs it) but a kink
+// at zero that a train-mode forward differentiates.  v + comp * |v| with comp = n_mma * 2^-25 removes the whole effect in
+// the A-GEM drop-in case (whole update vector 4.27e-5 off the live reference, exactly the fp32 kernels' 4.26e-5, against
+// 1.0e-2 without) but over-corrects on zero-mean random data (rms against fp64 2.4e-7 -> 6.5e-7 .. 1.7e-6,
+// tools/tcp_chain_accuracy.py) and breaks the golden-state gradient test: c depends on how the partial sums grow.  Until it
+// is modelled properly the train-mode forward stays on the fp32 kernels (conv_tcp_mode_allowed below).
 template <int NT>
 __device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NT], float comp = 0.f) {
   uint32_t r[NT];
@@ -524,8 +526,8 @@ int launch_tcp(ConvArgs a, cudaStream_t stream) {
     // class went from 4.15 to 4.3 ms per step pair -- the loaders were not the bound either -- and was reverted.
     const char* e = getenv("B200OCL_TCP_CHAIN");
     a.tp_chain = (e && e[0] == '3') ? 3 : 1;
-    const char* db = getenv("B200OCL_TCP_DEBIAS");      // multiplier of the rounding compensation (default 1, 0 = off)
-    a.tp_debias = db ? (float)atof(db) : 1.f;
+    const char* db = getenv("B200OCL_TCP_DEBIAS");      // multiplier of the experimental rounding compensation (default 0 = off)
+    a.tp_debias = db ? (float)atof(db) : 0.f;
   }
   if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) a.tp_bs = 4;
   if (tcp_smem_bytes<NT>(G0, a.tp_bn, a.tp_slices, a.tp_ps, a.tp_bs) > limit) { a.tp_ps = 2; a.tp_bs = 6; }
@@ -557,15 +559,16 @@ int launch_tcp(ConvArgs a, cudaStream_t stream) {
 bool conv_tcp_mode_allowed(const ConvArgs& a) {
   {
     // Which launch kinds take the tensor-core path: bit 0 eval features, bit 1 train-mode forward, bit 2 data gradient
-    // (B200OCL_TCP_MODES, default 7 = all).  The switch exists because of a round-2 finding (tests/test_gpu_dropin.py, A-GEM
-    // case against the live reference): WITHOUT the rounding compensation of tmem_accumulate() the train-mode forward on this
-    // path puts conv1.weight's update 1.0e-2 off the reference and only 8 % of the tensors inside 1e-3, while modes 1 and 5
-    // (train-mode forward on the fp32 kernels) give 5e-5.  With the compensation all three kinds are as good as fp32.
-    // Step pair: 8.59 ms (7) / 8.87 ms (5) / 9.26 ms (1).
+    // (B200OCL_TCP_MODES).  Default 5 = eval + data gradient.  Measured in round 2 against the live reference
+    // (tests/test_gpu_dropin.py, A-GEM case, one batch-10 step from torch's default initialisation): with the TRAIN-MODE
+    // FORWARD on this path the update of conv1.weight is 1.0e-2 off the reference (whose own one-ulp spread is 4e-6) and
+    // only 8 % of the tensors are inside 1e-3; with it on the fp32 kernels every tensor is inside 5e-5 -- and it makes no
+    // difference whether eval features and data gradients use the tensor path (modes 1 and 5 give the same 5e-5).  Cause:
+    // the downward rounding of the TMEM accumulate, see tmem_accumulate().  Step pair: 8.59 ms (7) / 8.87 (5) / 9.26 (1).
     static int modes = -1;
     if (modes < 0) {
       const char* m = getenv("B200OCL_TCP_MODES");
-      modes = (m && m[0] >= '0' && m[0] <= '7') ? (m[0] - '0') : 7;
+      modes = (m && m[0] >= '0' && m[0] <= '7') ? (m[0] - '0') : 5;
     }
     const int bit = a.mode == CONV_EVAL ? 1 : (a.mode == CONV_TRAIN ? 2 : 4);
     return (modes & bit) != 0;
