@@ -53,13 +53,15 @@ using umma::bulk_g2s;
 
 // acc += the NT fp32 columns of this warp's 32 TMEM lanes: all loads issued, one wait
 // comp: EXPERIMENTAL compensation of the TMEM accumulate's rounding (B200OCL_TCP_DEBIAS, default off).  Round-2 finding:
-// tcgen05 kind::tf32 accumulation rounds every accumulate step DOWN (toward -inf), so a read-out value is z - c|z| for a
+// tcgen05 kind::tf32 accumulation truncates at every accumulate step, so a read-out value behaves like z - c|z| for a
 // small data-dependent c -- not a scale factor (a relative correction changes nothing, BatchNorm absorbs it) but a kink
 // at zero that a train-mode forward differentiates.  v + comp * |v| with comp = n_mma * 2^-25 removes the whole effect in
 // the A-GEM drop-in case (whole update vector 4.27e-5 off the live reference, exactly the fp32 kernels' 4.26e-5, against
 // 1.0e-2 without) but over-corrects on zero-mean random data (rms against fp64 2.4e-7 -> 6.5e-7 .. 1.7e-6,
 // tools/tcp_chain_accuracy.py) and breaks the golden-state gradient test: c depends on how the partial sums grow.  Until it
-// is modelled properly the train-mode forward stays on the fp32 kernels (conv_tcp_mode_allowed below).
+// is modelled properly the train-mode forward stays on the fp32 kernels (conv_tcp_mode_allowed below).  (Accumulating odd
+// taps negated -- a_negate, idesc bit 13 -- and subtracting them at promotion gives bit-identical results: the rounding is
+// sign-symmetric, i.e. a truncation of the magnitude, so alternating signs cannot cancel it.)
 template <int NT>
 __device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NT], float comp = 0.f) {
   uint32_t r[NT];
