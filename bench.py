@@ -291,6 +291,11 @@ def profile_step(step_fn, i):
                                  '32x32): 17.3 MB per launch for 17.2 MB of input; see profiles/r01_v4_conv_tcp.md'
                                  if top == 'conv_tcp' else None),
                 'share_of_step': c['ms'] / total_ms, 'avg_launch_us': 1e3 * c['ms'] / max(c['launches'], 1)}
+        if top not in ('conv_tcp', 'conv_tc', 'conv_tc_train'):
+            # fp32 CUDA-core kernel: the pipe that bounds it is the FMA pipe, not the tensor pipe
+            fp32_peak = 148 * 128 * 2 * 1965.0e6 / 1e12
+            roof['fp32_fma'] = {'achieved_tflops': achieved, 'peak_tflops': fp32_peak, 'frac': achieved / fp32_peak,
+                                'peak_source': '148 SMs x 128 FMA lanes x 2 x 1965 MHz'}
         if top == 'conv_tcp':
             # issued work: 3 TF32 passes per useful FLOP, by-product halo rows and padded channel slots (x3.4 at these shapes);
             # the TF32 dense peak is half of the measured bf16 figure

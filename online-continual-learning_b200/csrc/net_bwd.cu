@@ -927,7 +927,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
   };
 
   // dz double buffer + fork / join (see bwd_async above)
-  BwdAsync* as = bwd_async();
+  BwdAsync* as = g_prof_on ? nullptr : bwd_async();   // per-launch profiling (bench.py) wants serial launches
   float* dzbuf[2] = {w.g2, w.g4};
   bool pending[2] = {false, false};
   int cur = 0;
