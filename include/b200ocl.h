@@ -14,7 +14,7 @@
  *   - fp32 data, int64 labels/indices (the reference's dtypes, data_utils.py:41,
  *     buffer.py:23);
  *   - no hidden allocation: scratch is caller-provided, sized by the matching
- *     *_workspace_bytes() query (must be 256-byte aligned);
+ *     *_workspace_bytes() query (must be 256-byte aligned); kernel attributes are cached per device;
  *   - every function returns 0 on success or a B200OCL_E* code; the message is
  *     available from b200ocl_last_error() (thread-local); nothing throws;
  *   - launches are asynchronous on `stream`; no function synchronises.
@@ -190,7 +190,10 @@ int b200ocl_net_forward_train(const b200ocl_net_desc* desc, const b200ocl_net_st
 
 /* loss.backward() for the forward kept in `workspace` (same x): dout [N,out_dim] -> st->grads
  * (overwritten, or added to when accumulate != 0 -- exp_replay.py:55,77 accumulate two
- * backward passes before one opt.step()). */
+ * backward passes before one opt.step()).
+ * The weight-gradient launches run on a helper stream that is forked from / joined into `stream` with events (captured
+ * as parallel branches when `stream` is being captured into a CUDA graph); the helper stream and its four events are the
+ * one piece of per-device state the library creates itself, on the first call (B200OCL_WG_ASYNC=0: everything on `stream`). */
 int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, const float* dout,
                          int N, void* workspace, size_t workspace_bytes, int accumulate, void* stream);
 
