@@ -180,18 +180,31 @@ def to_device_i64(arr, device):
 # Host-mirror updates that depend on device results (ASER's replacement decision) are deferred: the
 # decision is copied to pinned memory asynchronously and applied here, the next time any host-side
 # index logic runs -- by then the copy has long completed, so nothing waits on the GPU.
-_pending = []
+_pending = []        # [(owner id or None, fn)] in submission order
 _pinned_pool = []
 
 
-def defer(fn):
-    _pending.append(fn)
+def defer(fn, owner=None):
+    """Queue a host-mirror update.  `owner` (a Buffer) scopes it: reading another buffer's mirror does not wait for it."""
+    _pending.append((None if owner is None else id(owner), fn))
 
 
-def flush_pending():
+def flush_pending(owner=None):
+    """Apply queued updates in submission order: all of them (owner=None: the class-level sampler state is shared by
+    every buffer, as in the reference) or only those of one buffer."""
+    if owner is None:
+        while _pending:
+            _pending.pop(0)[1]()
+        return
+    oid = id(owner)
+    keep = []
     while _pending:
-        fn = _pending.pop(0)
-        fn()
+        o, fn = _pending.pop(0)
+        if o == oid:
+            fn()
+        else:
+            keep.append((o, fn))
+    _pending.extend(keep)
 
 
 def pinned_i64(n):
@@ -428,13 +441,13 @@ class Buffer(torch.nn.Module):
 
     @property
     def labels_host(self):
-        """numpy mirror of buffer_label; deferred device-decided updates are applied before it is read."""
-        flush_pending()
+        """numpy mirror of buffer_label; this buffer's deferred device-decided updates are applied before it is read."""
+        flush_pending(self)
         return self._labels_host
 
     @labels_host.setter
     def labels_host(self, value):
-        flush_pending()
+        flush_pending(self)
         self._labels_host = np.asarray(value, dtype=np.int64)
 
     def update(self, x, y, **kwargs):

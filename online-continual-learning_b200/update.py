@@ -167,7 +167,7 @@ class ASER_update(object):
                 CB._update_cache_now(buffer.buffer_label, out_dim, new_y=y_host[ind_cur], ind=ind_buffer)
                 buffer._labels_host[ind_buffer] = y_host[ind_cur]
             self._last_decision = (ind_cur, ind_buffer)
-        memory.defer(apply)
+        memory.defer(apply, owner=buffer)
 
     @property
     def last_decision(self):
