@@ -80,6 +80,21 @@ def _torch2_compat():
         return out
     random_retrieve._b200ocl_compat = True
     aser_update.random_retrieve = random_retrieve
+    # A second statement of the same kind: gss_greedy_update.py:43-46 index CPU tensors (`index`, `added_indx`) with
+    # the CUDA mask that torch.multinomial returned for CUDA probabilities (:38).  The name `torch` bound in that
+    # module becomes a proxy whose multinomial hands its result back on the CPU -- same call, same generator, same
+    # values; everything else is torch itself.
+    from utils.buffer import gss_greedy_update
+
+    class _TorchProxy(object):
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+        @staticmethod
+        def multinomial(*a, **k):
+            return torch.multinomial(*a, **k).cpu()
+    if not isinstance(gss_greedy_update.torch, _TorchProxy) and type(gss_greedy_update.torch).__name__ != '_TorchProxy':
+        gss_greedy_update.torch = _TorchProxy()
 
 
 def make_params(kind, **over):
@@ -98,6 +113,8 @@ def make_params(kind, **over):
         base.update(agent='ER', retrieve='MIR', update='random', eps_mem_batch=10)
     elif kind == 'agem':
         base.update(agent='AGEM', retrieve='random', update='random', eps_mem_batch=10)
+    elif kind == 'gss':
+        base.update(agent='ER', retrieve='random', update='GSS', eps_mem_batch=10, gss_mem_strength=10, gss_batch_size=10)
     elif kind == 'scr_aser':
         base.update(agent='SCR', retrieve='ASER', update='ASER', eps_mem_batch=100)
     else:

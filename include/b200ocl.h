@@ -112,6 +112,13 @@ size_t b200ocl_agem_project_workspace_bytes(void);
 int b200ocl_agem_project(const float* g, const float* g_ref, float* out, size_t n, float* dots_out, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* GSS-greedy scores (utils/buffer/gss_greedy_update.py:84,120 with cosine_similarity of buffer_utils.py:50-55): cosine
+ * similarity of the flat gradient g [n] with each of the K <= 64 stored gradients mem_grads [K,n] (cos_out [K], nullable)
+ * and their maximum (max_out [1], nullable).  Deterministic fp64 partials. */
+size_t b200ocl_grad_cosine_workspace_bytes(int K);
+int b200ocl_grad_cosine(const float* mem_grads, const float* g, int K, size_t n, float* cos_out, float* max_out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* Stream feeder (continuum/data_utils.py:38-54: ToTensor on every sample + DataLoader shuffle): dst[i] = image
  * src[perm[i]] converted uint8 HWC -> fp32 CHW in [0,1] with an IEEE division by 255 (bit-identical to the
  * reference's CPU ToTensor).  perm may be NULL (identity).  h*w*3 % 4 == 0. */
@@ -188,9 +195,15 @@ size_t b200ocl_net_train_workspace_bytes(const b200ocl_net_desc* desc, int N);
 int b200ocl_net_forward_train(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
                               float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* model.eval(); out = model.forward(x) WITH activations kept for a backward pass (utils/buffer/gss_greedy_update.py:16,
+ * 80-83, 118-120: GSS-greedy differentiates the network in eval mode): BatchNorm uses the running statistics, nothing is
+ * updated.  Its backward is b200ocl_net_backward with bit 1 of `accumulate` set. */
+int b200ocl_net_forward_evalgrad(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
+                                 float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* loss.backward() for the forward kept in `workspace` (same x): dout [N,out_dim] -> st->grads
  * (overwritten, or added to when accumulate != 0 -- exp_replay.py:55,77 accumulate two
- * backward passes before one opt.step()).
+ * backward passes before one opt.step()).  accumulate bit 1 (value 2): the forward was b200ocl_net_forward_evalgrad.
  * The weight-gradient launches run on a helper stream that is forked from / joined into `stream` with events (captured
  * as parallel branches when `stream` is being captured into a CUDA graph); the helper stream and its four events are the
  * one piece of per-device state the library creates itself, on the first call (B200OCL_WG_ASYNC=0: everything on `stream`). */

@@ -29,6 +29,8 @@ SIGNATURES = {
     'b200ocl_linear_argmax': (c_int, [P, c_int, c_int, P, P, c_int, P, P, P, P]),
     'b200ocl_agem_project_workspace_bytes': (c_size_t, []),
     'b200ocl_agem_project': (c_int, [P, P, P, c_size_t, P, P, c_size_t, P]),
+    'b200ocl_grad_cosine_workspace_bytes': (c_size_t, [c_int]),
+    'b200ocl_grad_cosine': (c_int, [P, P, c_int, c_size_t, P, P, P, c_size_t, P]),
     'b200ocl_sgd_step': (c_int, [P, P, P, c_size_t, c_float, c_float, P]),
     # ResNet engine: descriptor / state / info structs are passed by pointer (see engine.py)
     'b200ocl_net_query': (c_int, [P, P]),
@@ -38,6 +40,7 @@ SIGNATURES = {
     'b200ocl_net_features_eval': (c_int, [P, P, P, c_int, P, P, c_size_t, P]),
     'b200ocl_net_train_workspace_bytes': (c_size_t, [P, c_int]),
     'b200ocl_net_forward_train': (c_int, [P, P, P, c_int, P, P, c_size_t, P]),
+    'b200ocl_net_forward_evalgrad': (c_int, [P, P, P, c_int, P, P, c_size_t, P]),
     'b200ocl_net_backward': (c_int, [P, P, P, P, c_int, P, c_size_t, c_int, P]),
     'b200ocl_net_sgd_step': (c_int, [P, P, c_float, c_float, P, P]),
     'b200ocl_ce_loss': (c_int, [P, P, c_int, c_int, P, P, P, P, P]),

@@ -235,6 +235,59 @@ __global__ void __launch_bounds__(256) agem_apply_kernel(const float* __restrict
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = project ? g[i] - coef * gref[i] : g[i];
 }
+
+// GSS-greedy scores (utils/buffer/gss_greedy_update.py:84,120; buffer_utils.py:50-55): cosine similarity of a flat gradient g
+// with each of K stored gradients, and the maximum.  Launch 1: per-CTA fp64 partials of the K dot products, the K squared
+// norms and |g|^2 over the CTA's slice of the 1.1 M parameters; launch 2: partials reduced in CTA order (deterministic).
+constexpr int GC_MAX_K = 64;
+__global__ void __launch_bounds__(256) grad_cosine_partial_kernel(const float* __restrict__ mem, const float* __restrict__ g, int K,
+                                                                  size_t n, double* __restrict__ part) {
+  __shared__ double s_red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* my = part + (size_t)blockIdx.x * (2 * K + 1);
+  for (int q = 0; q <= 2 * K; ++q) {
+    double acc = 0.0;
+    const float* row = (q < K) ? mem + (size_t)q * n : (q < 2 * K ? mem + (size_t)(q - K) * n : g);
+    const float* other = (q < K) ? g : row;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+      acc += (double)row[i] * (double)other[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_red[w];
+      my[q] = t;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void grad_cosine_final_kernel(const double* __restrict__ part, int n_part, int K, float eps, float* __restrict__ cos_out,
+                                         float* __restrict__ max_out) {
+  __shared__ float s_cos[GC_MAX_K];
+  const int k = threadIdx.x;
+  double ng = 0.0;
+  for (int b = 0; b < n_part; ++b) ng += part[(size_t)b * (2 * K + 1) + 2 * K];
+  if (k < K) {
+    double dot = 0.0, nm = 0.0;
+    for (int b = 0; b < n_part; ++b) {
+      dot += part[(size_t)b * (2 * K + 1) + k];
+      nm += part[(size_t)b * (2 * K + 1) + K + k];
+    }
+    const float den = fmaxf(sqrtf((float)nm) * sqrtf((float)ng), eps);     // (w1 * w2.t()).clamp(min=eps)
+    s_cos[k] = (float)dot / den;
+    if (cos_out) cos_out[k] = s_cos[k];
+  }
+  __syncthreads();
+  if (k == 0 && max_out) {
+    float m = s_cos[0];
+    for (int j = 1; j < K; ++j) m = fmaxf(m, s_cos[j]);
+    *max_out = m;
+  }
+}
 }  // namespace
 }  // namespace b200ocl
 
@@ -316,6 +369,33 @@ int b200ocl_agem_project(const float* g, const float* g_ref, float* out, size_t 
   B200OCL_LAUNCHED();
   B200OCL_PROF("misc", 12.0 * n, stream);
   agem_apply_kernel<<<grid, 256, 0, stream>>>(g, g_ref, n, part, grid, out, dots_out);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
+
+size_t b200ocl_grad_cosine_workspace_bytes(int K) {
+  if (K < 0) K = 0;
+  return (size_t)296 * (2 * (size_t)K + 1) * sizeof(double) + 256;
+}
+
+int b200ocl_grad_cosine(const float* mem_grads, const float* g, int K, size_t n, float* cos_out, float* max_out, void* workspace,
+                        size_t workspace_bytes, void* stream_) {
+  using namespace b200ocl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200OCL_CHECK_ARG(K >= 1 && K <= GC_MAX_K && n >= 1, "need 1 <= K <= 64 and n >= 1");
+  B200OCL_CHECK_ARG(mem_grads && g && (cos_out || max_out), "null pointer");
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < b200ocl_grad_cosine_workspace_bytes(K)) {
+    set_error("b200ocl_grad_cosine: workspace missing, misaligned or smaller than %zu bytes", b200ocl_grad_cosine_workspace_bytes(K));
+    return B200OCL_EWORKSPACE;
+  }
+  int grid = 2 * sm_count();
+  if (grid > 296) grid = 296;
+  double* part = static_cast<double*>(workspace);
+  B200OCL_PROF("misc", 4.0 * (double)n * (2.0 * K + 1.0), stream);
+  grad_cosine_partial_kernel<<<grid, 256, 0, stream>>>(mem_grads, g, K, n, part);
+  B200OCL_LAUNCHED();
+  B200OCL_PROF("misc", 8.0 * grid * (2.0 * K + 1.0), stream);
+  grad_cosine_final_kernel<<<1, GC_MAX_K, 0, stream>>>(part, grid, K, 1e-8f, cos_out, max_out);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
 }

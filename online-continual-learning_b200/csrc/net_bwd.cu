@@ -43,6 +43,7 @@ struct BnBwdArgs {
   float* dgamma;
   float* dbeta;
   int accumulate;
+  int eval_stats;   // BN in eval mode: the statistics are constants, no mean / covariance terms in dz
   float* coef;  // [3][C]: gamma*invstd, mean(g), mean(g*xhat)
   float* dz;
   float* gout;  // nullable: masked gradient g (identity-shortcut branch)
@@ -146,8 +147,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
       a.dbeta[tid] = (float)db;
     }
     a.coef[tid] = a.gamma[tid] * a.invstd[tid];
-    a.coef[a.C + tid] = (float)(db / (double)a.M);
-    a.coef[2 * a.C + tid] = (float)(dg / (double)a.M);
+    a.coef[a.C + tid] = a.eval_stats ? 0.f : (float)(db / (double)a.M);
+    a.coef[2 * a.C + tid] = a.eval_stats ? 0.f : (float)(dg / (double)a.M);
   }
 }
 
@@ -293,8 +294,8 @@ __global__ void __launch_bounds__(256, 1) bn_bwd_fused_kernel(BnBwdArgs a) {
         a.dbeta[tid] = (float)db;
       }
       a.coef[tid] = a.gamma[tid] * a.invstd[tid];
-      a.coef[a.C + tid] = (float)(db / (double)a.M);
-      a.coef[2 * a.C + tid] = (float)(dg / (double)a.M);
+      a.coef[a.C + tid] = a.eval_stats ? 0.f : (float)(db / (double)a.M);
+      a.coef[2 * a.C + tid] = a.eval_stats ? 0.f : (float)(dg / (double)a.M);
     }
     __threadfence();
     __syncthreads();
@@ -809,6 +810,8 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     set_error("b200ocl_net_backward: workspace missing, misaligned or too small");
     return B200OCL_EWORKSPACE;
   }
+  const int eval_stats = (accumulate >> 1) & 1;   // bit 1 of `accumulate`: backward of b200ocl_net_forward_evalgrad
+  accumulate &= 1;
   const int sms = sm_count();
   TrainWs w = train_ws(p, N, workspace, sms);
   unsigned int* counters = w.counters + NET_COUNTERS / 2;
@@ -863,6 +866,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
     a.dgamma = st->grads + b.g_off;
     a.dbeta = st->grads + b.b_off;
     a.accumulate = accumulate;
+    a.eval_stats = eval_stats;
     a.coef = coef;
     a.dz = dz;
     a.gout = gout;

@@ -467,8 +467,20 @@ __global__ void __launch_bounds__(256) bn_restat_kernel(const float* __restrict_
   }
 }
 
+// Eval-statistics forward (GSS-greedy differentiates the network in eval mode, gss_greedy_update.py:16): the
+// "saved" statistics that bn_apply and the backward use are the RUNNING ones; the batch statistics the train-mode
+// convolution computes go to a throw-away buffer and the running statistics are left alone.
+__global__ void bn_save_running_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar, float eps, int C,
+                                       float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    save_mean[c] = rmean[c];
+    save_invstd[c] = 1.0f / sqrtf(rvar[c] + eps);
+  }
+}
+
 int conv_train(const NetPlan& p, const b200ocl_net_state& st, const TrainWs& w, int ci, int N, const float* in,
-               cudaStream_t stream) {
+               cudaStream_t stream, bool eval_stats = false) {
   ConvArgs a;
   const ConvL& c = p.conv[ci];
   fill_conv_common(a, c, N, in, st.packed, w.z + (size_t)N * c.act_off);
@@ -478,9 +490,14 @@ int conv_train(const NetPlan& p, const b200ocl_net_state& st, const TrainWs& w, 
   a.counter = w.counters + 8 * ci;   // up to 8 channel tiles per conv (160 = 8 x 20)
   a.save_mean = w.save + b.save_off;
   a.save_invstd = w.save + b.save_off + b.c;
-  a.run_mean = st.bn_stats + b.stat_off;
-  a.run_var = st.bn_stats + b.stat_off + b.c;
+  a.run_mean = eval_stats ? w.run_scratch : st.bn_stats + b.stat_off;
+  a.run_var = eval_stats ? w.run_scratch + 1024 : st.bn_stats + b.stat_off + b.c;
   const int rc = ci == 0 ? launch_stem(a, stream) : launch_conv(a, stream);
+  if (rc == 0 && eval_stats) {
+    bn_save_running_kernel<<<(b.c + 127) / 128, 128, 0, stream>>>(st.bn_stats + b.stat_off, st.bn_stats + b.stat_off + b.c, a.eps,
+                                                                   b.c, a.save_mean, a.save_invstd);
+    B200OCL_LAUNCHED();
+  }
   static int restat = -1;
   if (restat < 0) {
     const char* e = getenv("B200OCL_RESTAT");
@@ -781,8 +798,8 @@ size_t b200ocl_net_train_workspace_bytes(const b200ocl_net_desc* desc, int N) {
   return train_ws(p, N > 0 ? N : 1, nullptr, sm_count()).bytes;
 }
 
-int b200ocl_net_forward_train(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
-                              float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+static int net_forward_impl(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N, float* out,
+                            void* workspace, size_t workspace_bytes, void* stream_, bool ev) {
   using namespace b200ocl;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NetPlan p;
@@ -796,24 +813,24 @@ int b200ocl_net_forward_train(const b200ocl_net_desc* desc, const b200ocl_net_st
   }
   TrainWs w = train_ws(p, N, workspace, sm_count());
   B200OCL_CUDA(cudaMemsetAsync(w.counters, 0, NET_COUNTERS * sizeof(unsigned int), stream));
-  if ((rc = conv_train(p, *st, w, 0, N, x, stream))) return rc;
+  if ((rc = conv_train(p, *st, w, 0, N, x, stream, ev))) return rc;
   if ((rc = bn_apply_train(p, *st, w, 0, N, -1, nullptr, stream))) return rc;
   const float* cur = w.a + (size_t)N * p.conv[0].act_off;
   for (int b = 0; b < 8; ++b) {
     const BlockL& B = p.blk[b];
-    if ((rc = conv_train(p, *st, w, B.c1, N, cur, stream))) return rc;
+    if ((rc = conv_train(p, *st, w, B.c1, N, cur, stream, ev))) return rc;
     if ((rc = bn_apply_train(p, *st, w, B.c1, N, -1, nullptr, stream))) return rc;
     const float* a1 = w.a + (size_t)N * p.conv[B.c1].act_off;
-    if ((rc = conv_train(p, *st, w, B.c2, N, a1, stream))) return rc;
+    if ((rc = conv_train(p, *st, w, B.c2, N, a1, stream, ev))) return rc;
     if (B.sc >= 0) {
-      if ((rc = conv_train(p, *st, w, B.sc, N, cur, stream))) return rc;
+      if ((rc = conv_train(p, *st, w, B.sc, N, cur, stream, ev))) return rc;
       if ((rc = bn_apply_train(p, *st, w, B.c2, N, B.sc, nullptr, stream))) return rc;
     } else {
       if ((rc = bn_apply_train(p, *st, w, B.c2, N, -1, cur, stream))) return rc;
     }
     cur = w.a + (size_t)N * p.conv[B.c2].act_off;
   }
-  if (st->bn_tracked) {
+  if (st->bn_tracked && !ev) {
     B200OCL_PROF("misc", 16.0 * p.n_conv, stream);
     bump_tracked_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<long long*>(st->bn_tracked), p.n_conv);
     B200OCL_LAUNCHED();
@@ -824,6 +841,16 @@ int b200ocl_net_forward_train(const b200ocl_net_desc* desc, const b200ocl_net_st
                                                        p.pooled_w);
   B200OCL_LAUNCHED();
   return head_forward(p, *st, w.feat, N, w.hid, w.proj, out, stream);
+}
+
+int b200ocl_net_forward_train(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
+                              float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  return net_forward_impl(desc, st, x, N, out, workspace, workspace_bytes, stream_, false);
+}
+
+int b200ocl_net_forward_evalgrad(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
+                                 float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  return net_forward_impl(desc, st, x, N, out, workspace, workspace_bytes, stream_, true);
 }
 
 int b200ocl_ce_loss(const float* logits, const int64_t* labels, int N, int C, float* loss, float* per_sample,

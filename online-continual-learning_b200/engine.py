@@ -230,20 +230,21 @@ class Engine:
                 self._train_ws[key] = ws
         return ws
 
-    def forward_train(self, x, ws=None, state=None, slot=0):
+    def forward_train(self, x, ws=None, state=None, slot=0, eval_stats=False):
         """model.train(); model.forward(x).  Returns (out [N,out_dim], workspace kept for backward).
-        """
+        eval_stats=True: model.eval() forward that can be differentiated (running statistics, nothing updated)."""
         x = self._x(x)
         n = x.shape[0]
-        graphed = _GRAPHS and ws is None and state is None and (n, slot) in self._train_ws
+        graphed = _GRAPHS and ws is None and state is None and (n, slot) in self._train_ws and not eval_stats
         if ws is None:
             ws = self.train_workspace(n, slot)
         st = state or self.state
 
         def launch(xin, out):
-            rc = _lib().b200ocl_net_forward_train(ctypes.byref(self.desc), ctypes.byref(st.c), xin.data_ptr(), n,
-                                                  out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
-            _native.check(rc, 'b200ocl_net_forward_train')
+            fn = _lib().b200ocl_net_forward_evalgrad if eval_stats else _lib().b200ocl_net_forward_train
+            rc = fn(ctypes.byref(self.desc), ctypes.byref(st.c), xin.data_ptr(), n, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                    _stream())
+            _native.check(rc, 'b200ocl_net_forward_evalgrad' if eval_stats else 'b200ocl_net_forward_train')
 
         if graphed:
             key = ('fwd', n, slot)
@@ -258,8 +259,9 @@ class Engine:
         launch(x, out)
         return out, ws
 
-    def backward(self, x, dout, ws, accumulate=False):
-        """loss.backward() for the forward of the same x kept in ws; fills (or adds to) the grad arena."""
+    def backward(self, x, dout, ws, accumulate=False, eval_stats=False):
+        """loss.backward() for the forward of the same x kept in ws; fills (or adds to) the grad arena.
+        eval_stats=True: the forward was forward_train(..., eval_stats=True)."""
         _need_cuda(dout)
         x = self._x(x)
         dout = dout.detach().to(torch.float32).contiguous()
@@ -269,11 +271,11 @@ class Engine:
 
         def launch(xin, din):
             rc = _lib().b200ocl_net_backward(ctypes.byref(self.desc), ctypes.byref(self.state.c), xin.data_ptr(),
-                                             din.data_ptr(), n, ws.data_ptr(), ws.numel(), 1 if accumulate else 0,
-                                             _stream())
+                                             din.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                                             (1 if accumulate else 0) | (2 if eval_stats else 0), _stream())
             _native.check(rc, 'b200ocl_net_backward')
 
-        slot = next((k[1] for k, w in self._train_ws.items() if w is ws and k[0] == n), None) if _GRAPHS else None
+        slot = next((k[1] for k, w in self._train_ws.items() if w is ws and k[0] == n), None) if (_GRAPHS and not eval_stats) else None
         fwd = self._graphs.get(('fwd', n, slot)) if slot is not None else None
         if fwd is not None:
             # the images are the static copy the graphed forward read (same data as x)

@@ -208,6 +208,30 @@ def agem_project(g, g_ref, out=None, want_dots=False):
     return (out, dots) if want_dots else out
 
 
+GRAD_COSINE_MAX_K = 64
+
+
+def grad_cosine(mem_grads, g, max_out=None):
+    """(cos [K], max [1]): cosine similarity of the flat gradient g with each stored gradient and their maximum
+    (gss_greedy_update.py:84,120 with buffer_utils.py:50-55).  max_out: a one-element fp32 device tensor (view) to
+    write the maximum into."""
+    _need_cuda(mem_grads, g)
+    mem_grads, g = _f32(mem_grads), _f32(g).reshape(-1)
+    K, n = mem_grads.shape
+    if g.numel() != n:
+        raise ValueError('gradient length mismatch')
+    cos = torch.empty(K, dtype=torch.float32, device=g.device)
+    if max_out is None:
+        max_out = torch.empty(1, dtype=torch.float32, device=g.device)
+    elif max_out.numel() != 1 or max_out.dtype != torch.float32 or not max_out.is_cuda:
+        raise ValueError('max_out must be a one-element fp32 CUDA tensor')
+    lib = _native.lib()
+    ws = _workspace(lib.b200ocl_grad_cosine_workspace_bytes(K), g.device)
+    rc = lib.b200ocl_grad_cosine(_ptr(mem_grads), _ptr(g), K, n, _ptr(cos), _ptr(max_out), _ptr(ws), ws.numel(), _stream())
+    _native.check(rc, 'b200ocl_grad_cosine')
+    return cos, max_out
+
+
 def scatter_rows(dst, idx, src):
     """dst[idx[i]] = src[i] over the first dimension (buffer_img[idx] = x)."""
     _need_cuda(dst, idx, src)

@@ -11,7 +11,7 @@ Every other agent / plugin of the reference stays registered and untouched.
 """
 from .learners import AGEM, ExperienceReplay, SupContrastReplay
 from .retrieve import ASER_retrieve, MIR_retrieve, Random_retrieve
-from .update import ASER_update, Reservoir_update
+from .update import ASER_update, GSSGreedyUpdate, Reservoir_update
 
 agents = {
     'ER': ExperienceReplay,
@@ -27,6 +27,7 @@ retrieve_methods = {
 
 update_methods = {
     'random': Reservoir_update,
+    'GSS': GSSGreedyUpdate,
     'ASER': ASER_update,
 }
 

@@ -174,3 +174,116 @@ class ASER_update(object):
         """(positions in the current batch, buffer slots they replaced) of the latest update."""
         memory.flush_pending()
         return self._last_decision
+
+
+class GSSGreedyUpdate(object):
+    """GSS-greedy (utils/buffer/gss_greedy_update.py:7-124) on the flat gradient arena.
+
+    Every gradient the rule needs is one differentiable EVAL-mode pass of the engine
+    (`b200ocl_net_forward_evalgrad` + `b200ocl_net_backward` with the eval-statistics bit: the reference switches the
+    model to eval() before it differentiates it, gss_greedy_update.py:16) that leaves the gradient of all parameters,
+    in parameters() order, in the engine's gradient arena -- the vector get_grad_vector() assembles tensor by tensor
+    (buffer_utils.py:58-73).  The cosine similarities against the stored memory gradients and their maximum are one
+    kernel (`b200ocl_grad_cosine`).  The random decisions are the reference's calls on the reference's generators:
+    torch.randperm / the first torch.multinomial on the CPU generator, the replacement lottery on the generator of the
+    scores' device."""
+
+    SLOT = 5          # workspace slot of the engine that these passes use (the learners use 0, 1, 3)
+
+    def __init__(self, params):
+        super().__init__()
+        self.mem_strength = params.gss_mem_strength
+        self.gss_batch_size = params.gss_batch_size
+        dev = 'cuda' if torch.cuda.is_available() else 'cpu'
+        self.buffer_score = torch.zeros(params.mem_size, dtype=torch.float32, device=dev)
+        self.last_batch_sim = None        # kept for inspection (tests: near-zero decisions)
+        self.last_replaced = None
+
+    # ---- one gradient: model.zero_grad(); F.cross_entropy(model.forward(x), y).backward()  (:80-83, :100-103, :117-119)
+    def _gradient(self, eng, x, y):
+        from .engine import ce_loss
+        logits, ws = eng.forward_train(x, slot=self.SLOT, eval_stats=True)
+        ce = ce_loss(logits, y, want_grad=True)
+        eng.backward(x, ce['dlogits'], ws, eval_stats=True)
+        return eng.state.grads
+
+    def update(self, buffer, x, y, **kwargs):
+        eng = engine_of(buffer.model)
+        y_host = _host_labels(y, kwargs)
+        buffer.model.eval()                                                     # :16
+        x = x.detach().to(torch.float32).contiguous()
+        self.last_replaced = None
+        place_left = buffer.buffer_img.size(0) - buffer.current_index
+        if place_left <= 0:                                                     # buffer is full (:22)
+            batch_sim, mem_grads = self.get_batch_sim(buffer, eng, x, y)
+            self.last_batch_sim = float(batch_sim)                              # the reference's `if batch_sim < 0` reads it too
+            if self.last_batch_sim < 0:
+                buffer_score = self.buffer_score[:buffer.current_index].cpu()
+                buffer_sim = (buffer_score - torch.min(buffer_score)) / \
+                             ((torch.max(buffer_score) - torch.min(buffer_score)) + 0.01)
+                index = torch.multinomial(buffer_sim, x.size(0), replacement=False)          # CPU generator (:30)
+                batch_item_sim = self.get_each_batch_sample_sim(buffer, eng, mem_grads, x, y)
+                index_dev = index.to(self.buffer_score.device)
+                scaled_batch_item_sim = ((batch_item_sim + 1) / 2).unsqueeze(1)
+                buffer_repl_batch_sim = ((self.buffer_score[index_dev] + 1) / 2).unsqueeze(1)
+                outcome = torch.multinomial(torch.cat((scaled_batch_item_sim, buffer_repl_batch_sim), dim=1), 1,
+                                            replacement=False)                               # the scores' device generator (:38)
+                sub = outcome.squeeze(1).bool().cpu().numpy()
+                slots = index.numpy()[sub]
+                src = np.flatnonzero(sub)
+                self.last_replaced = (src, slots)
+                if slots.size:
+                    src_t = to_device_i64(src, x.device)
+                    buffer.write(slots, ops.gather_rows(x, src_t) if x.is_cuda else x[src_t],
+                                 ops.gather_rows(y, src_t) if y.is_cuda else y[src_t], y_host[src])
+                    new_scores = ops.gather_rows(batch_item_sim, src_t) if batch_item_sim.is_cuda else batch_item_sim[src_t]
+                    slots_t = to_device_i64(slots, self.buffer_score.device)
+                    if self.buffer_score.is_cuda:
+                        ops.scatter_rows(self.buffer_score, slots_t, new_scores)
+                    else:
+                        self.buffer_score[slots_t] = new_scores
+        else:
+            offset = min(place_left, x.size(0))
+            x, y, y_host = x[:offset], y[:offset], y_host[:offset]
+            if buffer.current_index == 0:                                       # first insertion (:52-53)
+                batch_sample_memory_cos = torch.zeros(x.size(0)) + 0.1
+            else:
+                mem_grads = self.get_rand_mem_grads(buffer, eng)
+                batch_sample_memory_cos = self.get_each_batch_sample_sim(buffer, eng, mem_grads, x, y)
+            s, e = buffer.current_index, buffer.current_index + offset
+            buffer.buffer_img[s:e].copy_(x)
+            buffer.buffer_label[s:e].copy_(y)
+            buffer.labels_host[s:e] = y_host
+            self.buffer_score[s:e].copy_(batch_sample_memory_cos)
+            buffer.current_index += offset
+        buffer.model.train()                                                    # :64
+
+    def get_batch_sim(self, buffer, eng, batch_x, batch_y):
+        """(score of the incoming batch [1], memory gradients [K, n_params])  (:66-85)."""
+        mem_grads = self.get_rand_mem_grads(buffer, eng)
+        g = self._gradient(eng, batch_x, batch_y)
+        _, batch_sim = ops.grad_cosine(mem_grads, g)
+        return batch_sim, mem_grads
+
+    def get_rand_mem_grads(self, buffer, eng):
+        """Gradients of num_mem_subs random memory minibatches (:87-107)."""
+        gss_batch_size = min(self.gss_batch_size, buffer.current_index)
+        num_mem_subs = min(self.mem_strength, buffer.current_index // gss_batch_size)
+        if num_mem_subs > ops.GRAD_COSINE_MAX_K:
+            raise ValueError('gss_mem_strength %d exceeds the kernel limit %d' % (num_mem_subs, ops.GRAD_COSINE_MAX_K))
+        mem_grads = torch.zeros((num_mem_subs, eng.info.n_params), dtype=torch.float32, device=eng.device)
+        shuffeled_inds = torch.randperm(buffer.current_index).numpy()            # CPU generator (:98)
+        for i in range(num_mem_subs):
+            bx, by, _ = buffer.gather(shuffeled_inds[i * gss_batch_size:i * gss_batch_size + gss_batch_size])
+            mem_grads[i].copy_(self._gradient(eng, bx, by))
+        return mem_grads
+
+    def get_each_batch_sample_sim(self, buffer, eng, mem_grads, batch_x, batch_y):
+        """Score of every sample of the batch: the largest cosine similarity of its own gradient with the memory
+        gradients (:109-124)."""
+        n = batch_x.size(0)
+        cosine_sim = torch.zeros(n, dtype=torch.float32, device=eng.device)
+        for i in range(n):
+            g = self._gradient(eng, batch_x[i:i + 1], batch_y[i:i + 1])
+            ops.grad_cosine(mem_grads, g, max_out=cosine_sim[i:i + 1])
+        return cosine_sim

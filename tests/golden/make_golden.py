@@ -474,14 +474,75 @@ def gen_steps():
         out[tag + '_lin_w'] = [prm for n_, prm in model.named_parameters() if n_.endswith('linear.weight') or n_ == 'head.2.weight'][-1].detach().numpy().copy()
     np.savez_compressed(os.path.join(HERE, 'steps.npz'), **out)
 
+# ----------------------------------------------------------------------------- GSS-greedy
+def gen_gss():
+    """Reference GSSGreedyUpdate (gss_greedy_update.py:7-124) driven through the reference Buffer on a seeded
+    Reduced_ResNet18 (CPU): three fill batches, then full-memory updates with unseen classes (batch_sim < 0: the
+    replacement lottery) and seen classes.  The inputs come from a numpy stream the test regenerates; the file
+    records the torch seed before every update, the scores, labels and the source of every slot afterwards."""
+    from utils import name_match  # noqa: F401  (resolves the reference's circular import first)
+    from utils.buffer.buffer import Buffer
+    from utils.buffer import gss_greedy_update
+    out = {}
+    spec = oresnet.Spec(32, 20, 10)
+    model, p, bn = _ref_model('cifar10', 'ER', None, spec, 77)
+    with torch.no_grad():          # a small classifier: softmax outputs near uniform, so the sign of a gradient cosine
+        model.linear.weight.mul_(0.02)   # follows the label overlap (the test applies the same two lines to the oracle state)
+        model.linear.bias.zero_()
+    mem, batch, n_upd = 30, 10, 8
+    params = SimpleNamespace(data='cifar10', cuda=False, mem_size=mem, update='GSS', retrieve='random',
+                             gss_mem_strength=10, gss_batch_size=10, buffer_tracker=False, eps_mem_batch=10)
+    buf = Buffer(model, params)
+    upd = buf.update_method
+    assert isinstance(upd, gss_greedy_update.GSSGreedyUpdate)
+    sims = []
+    orig = upd.get_batch_sim
+
+    def hook(*a, **k):
+        s, m = orig(*a, **k)
+        sims.append(float(s))
+        return s, m
+    upd.get_batch_sim = hook
+    rs = np.random.RandomState(770)
+    # slot -> (update number, position in that batch) of the sample it holds: the memory contents without the pixels
+    src = np.full((mem, 2), -1, dtype=np.int64)
+    labels, scores, srcs, batch_sim, ys = [], [], [], [], []
+    for u in range(n_upd):
+        x = torch.from_numpy(rs.rand(batch, 3, 32, 32).astype(np.float32))
+        lab = rs.randint(0, 3, batch)
+        y = torch.from_numpy(lab.astype(np.int64))
+        if u >= 3 and u % 2 == 1:
+            lab = lab + 3 + 3 * ((u // 2) % 2)   # classes the memory does not hold: with near-uniform softmax outputs the batch gradient
+            y = torch.from_numpy(lab.astype(np.int64))   # points away from the memory gradients (batch_sim < 0)
+        torch.manual_seed(1000 + u)
+        before_img = buf.buffer_img.clone()
+        n_sims = len(sims)
+        buf.update(x, y)
+        changed = (buf.buffer_img != before_img).flatten(1).any(1).nonzero().flatten().tolist()
+        for sl in changed:
+            pos = [i for i in range(batch) if torch.equal(buf.buffer_img[sl], x[i])]
+            assert len(pos) == 1
+            src[sl] = (u, pos[0])
+        ys.append(lab.astype(np.int64))
+        labels.append(buf.buffer_label.numpy().copy())
+        scores.append(upd.buffer_score.numpy().copy())
+        srcs.append(src.copy())
+        batch_sim.append(sims[-1] if len(sims) > n_sims else np.nan)
+    assert model.training                                   # the rule leaves the model in train mode (:64)
+    print('gss batch_sim', batch_sim)
+    assert any(b < 0 for b in batch_sim if b == b) and any(b >= 0 for b in batch_sim if b == b)
+    out.update(y=np.stack(ys), labels=np.stack(labels), scores=np.stack(scores), src=np.stack(srcs),
+               batch_sim=np.array(batch_sim), mem=np.int64(mem), batch=np.int64(batch), model_seed=np.int64(77),
+               data_seed=np.int64(770), torch_seed0=np.int64(1000))
+    np.savez_compressed(os.path.join(HERE, 'gss.npz'), **out)
+
 
 if __name__ == '__main__':
-    gen_knn_sv()
-    gen_supcon()
-    gen_resnet()
-    gen_aser()
-    gen_reservoir()
-    gen_steps()
+    only = sys.argv[2:]            # e.g. `make_golden.py /root/reference gss`: regenerate one file
+    for name, fn in (('knn_sv', gen_knn_sv), ('supcon', gen_supcon), ('resnet', gen_resnet), ('aser', gen_aser),
+                     ('reservoir', gen_reservoir), ('steps', gen_steps), ('gss', gen_gss)):
+        if not only or name in only:
+            fn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

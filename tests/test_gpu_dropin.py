@@ -77,9 +77,15 @@ def _same_rng(a, b):
 
 
 def _snapshot(agent):
-    return {'state': {k: v.detach().clone() for k, v in agent.model.state_dict().items()},
+    snap = {'state': {k: v.detach().clone() for k, v in agent.model.state_dict().items()},
             'label': agent.buffer.buffer_label.clone(), 'img': agent.buffer.buffer_img.clone(),
             'n_seen': agent.buffer.n_seen_so_far, 'index': agent.buffer.current_index, 'rng': _rng_states()}
+    if hasattr(agent.buffer.update_method, 'buffer_score'):         # GSS-greedy: the per-slot scores are part of the memory
+        snap['score'] = agent.buffer.update_method.buffer_score.clone()
+    return snap
+
+
+SCORE_TOL = 2e-3      # GSS scores are cosines of two 1.1 M-element gradients: absolute tolerance
 
 
 def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, noise=None, measure_noise=False, **over):
@@ -114,10 +120,29 @@ def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, noise=None, me
             if hasattr(agent, 'transform'):
                 agent.transform = Identity()              # the reference side runs the identity kornia stub
         mem = params.mem_size
+        gss = params.update == 'GSS'
         x = torch.from_numpy(rs.rand(mem, 3, hw, hw).astype(np.float32)).cuda()
-        y = torch.from_numpy(rs.randint(0, n_label, mem).astype(np.int64)).cuda()
-        agent.buffer.update(x, y)                         # fill phase through the plugin
+        y = torch.from_numpy(rs.randint(0, 3 if gss else n_label, mem).astype(np.int64)).cuda()
+        if gss:
+            # GSS scores every inserted sample against gradients of the memory so far (gss_greedy_update.py:47-62): the
+            # memory is filled batch by batch as a stream would (one call would leave all scores equal, and the
+            # reference's first multinomial then raises on an all-zero distribution)
+            for s0 in range(0, mem, params.batch):
+                agent.buffer.update(x[s0:s0 + params.batch], y[s0:s0 + params.batch])
+            prefill_score = agent.buffer.update_method.buffer_score.clone()
+            if ours:
+                ref_score = trace[0]['prefill_score']
+                err = float((prefill_score - ref_score).abs().max())
+                REPORT['%s/prefill_score_max_abs_err' % kind] = err
+                assert err <= SCORE_TOL, ('fill-phase scores', err)
+                assert torch.equal(agent.buffer.buffer_label, trace[0]['prefill_label'])
+                assert _same_rng(_rng_states(), trace[0]['prefill_rng']), 'the fill phase consumed different draws'
+                agent.buffer.update_method.buffer_score.copy_(ref_score)
+        else:
+            agent.buffer.update(x, y)                     # fill phase through the plugin
         prefill_img = agent.buffer.buffer_img.clone()
+        prefill_extra = ({'prefill_score': agent.buffer.update_method.buffer_score.clone(),
+                          'prefill_label': agent.buffer.buffer_label.clone(), 'prefill_rng': _rng_states()} if gss else {})
         before = {k: v.detach().clone() for k, v in agent.model.state_dict().items()}
         for c in range(n_calls):
             n = params.batch + 3                          # one step; the 3 extra samples exercise drop_last
@@ -125,6 +150,10 @@ def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, noise=None, me
             # every label occurs in every call when n_label is small: the reference's NCM evaluate indexes a
             # dict keyed by the labels seen in training with every buffer label (base.py:124-126)
             yt = rs.permutation(np.arange(n) % n_label).astype(np.int64)
+            if gss:
+                # classes the memory has not seen make the batch gradient point away from the memory gradients
+                # (batch_sim < 0: the replacement branch); classes it has seen do the opposite -- both are exercised
+                yt = rs.permutation(np.arange(n) % 3 + 3 * ((c + 1) % 3)).astype(np.int64)
             if measure_noise:
                 with torch.no_grad():
                     for prm in agent.model.parameters():
@@ -134,6 +163,8 @@ def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, noise=None, me
             agent.train_learner(xt, yt)
             torch.cuda.synchronize(); t_train += time.perf_counter() - t0
             snap = _snapshot(agent)
+            if c == 0:
+                snap.update(prefill_extra)
             if c in (n_calls // 2 - 1, n_calls - 1):
                 tests = [(rs.randint(0, 256, (96, hw, hw, 3)).astype(np.uint8), rs.permutation(np.arange(96) % n_label).astype(np.int64))
                          for _ in range(2)]
@@ -159,6 +190,13 @@ def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, noise=None, me
                     # (aser_update.py:84).  A different eviction is accepted only when it is such a tie: the slots
                     # evicted by one run and not by the other must have equal scores (<= 1e-5) in our ranking.
                     upd = agent.buffer.update_method
+                    if hasattr(upd, 'last_batch_sim'):
+                        # GSS-greedy replaces only when the batch's best cosine with the memory gradients is negative
+                        # (gss_greedy_update.py:25): a different memory is accepted only when that cosine sat on zero
+                        assert upd.last_batch_sim is not None and abs(upd.last_batch_sim) <= SCORE_TOL, \
+                            (tag, 'GSS wrote different slots', upd.last_batch_sim)
+                        REPORT.setdefault('%s/ties' % kind, []).append({'call': c, 'batch_sim': upd.last_batch_sim})
+                        break
                     assert hasattr(upd, 'last_sv_sum'), tag + ': different slots written by a non-ASER update'
                     prev_img = trace[c - 1]['img'] if c > 0 else prefill_img
                     ev_ref = set((ref['img'] != prev_img).flatten(1).any(1).nonzero().flatten().tolist())
@@ -180,6 +218,12 @@ def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, noise=None, me
                     assert scores.max() - scores.min() <= 1e-5 * max(1.0, float(np.abs(sv).max())), (tag, diff, scores)
                     REPORT.setdefault('%s/ties' % kind, []).append({'call': c, 'slots': diff, 'scores': scores.tolist()})
                     break           # the memories differ from here on: the run ends with the tie verified
+            if ours and 'score' in ref:
+                err = float((snap['score'] - ref['score']).abs().max())
+                REPORT['%s/score_max_abs_err' % kind] = max(REPORT.get('%s/score_max_abs_err' % kind, 0.0), err)
+                assert err <= SCORE_TOL, (tag, 'GSS scores', err)
+                REPORT.setdefault('%s/replaced_per_call' % kind, []).append(
+                    int((ref['label'] != (trace[c - 1]['label'] if c > 0 else trace[0]['prefill_label'])).sum()))
             spread = {'decisions_same': bool(decisions_same)}
             vec_num = vec_den = 0.0
             n_tensors = n_inside = 0
@@ -241,6 +285,8 @@ def _script(kind, ours, n_calls, n_label=100, seed=0, trace=None, noise=None, me
             if measure_noise and not decisions_same:      # the perturbed reference decided differently: realign its memory
                 agent.buffer.buffer_label.copy_(ref['label']); agent.buffer.buffer_img.copy_(ref['img'])
                 agent.buffer.n_seen_so_far, agent.buffer.current_index = ref['n_seen'], ref['index']
+            if 'score' in ref:
+                agent.buffer.update_method.buffer_score.copy_(ref['score'])
             before = {k: v.clone() for k, v in ref['state'].items()}
         name = 'b200ocl' if ours else ('reference_one_ulp' if measure_noise else 'reference')
         REPORT['%s/%s' % (kind, name)] = {'train_s': t_train, 'eval_s': t_eval, 'calls': n_calls}
@@ -275,6 +321,8 @@ CASES = [
     ('scr_aser', 4, 10, dict(n_smp_cls=2.0)),                              # SCR agent with the ASER plugins
     ('mir', 4, 100, dict(data='mini_imagenet', mem_size=10000)),           # config 4: 84x84
     ('agem', 4, 100, dict(mem_size=1000)),                                 # A-GEM on the flat gradient arena
+    # GSS-greedy -- eval-mode gradients on the flat arena, cosine scores, the reference's lotteries
+    ('gss', 6, 9, dict(data='cifar10', mem_size=200, learning_rate=0.05)),
     # review trick (agents/base.py:62-88; the published SCR setting): after_train replays the memory, gradients / 10
     ('scr', 3, 10, dict(mem_size=200, trick=dict(ref_harness.TRICK, review_trick=True))),
     ('er', 3, 10, dict(data='cifar10', mem_size=40, trick=dict(ref_harness.TRICK, review_trick=True))),

@@ -203,3 +203,33 @@ def test_reservoir_matches_reference(golden_dir):
     assert seen == int(g['n_seen'])
     np.testing.assert_array_equal(img, g['final_img'])
     np.testing.assert_array_equal(lab, g['final_label'])
+
+
+def test_gss_greedy_matches_reference(golden_dir):
+    """oracle/gss.py replays the reference GSSGreedyUpdate run recorded in gss.npz (fill phase, two replacement
+    lotteries, three updates that replace nothing): same labels, same slot sources, scores within 1e-4."""
+    from oracle import gss as ogss
+    g = _load(golden_dir, 'gss.npz')
+    mem, batch = int(g['mem']), int(g['batch'])
+    spec = oresnet.Spec(32, 20, 10)
+    p, bn = oresnet.seeded_state(spec, int(g['model_seed']))
+    p['linear.weight'] = p['linear.weight'] * 0.02          # the two lines make_golden.gen_gss applies to the reference model
+    p['linear.bias'] = torch.zeros_like(p['linear.bias'])
+    st = ogss.GSSState(spec, p, bn, mem, (3, 32, 32))
+    rs = np.random.RandomState(int(g['data_seed']))
+    src = np.full((mem, 2), -1, dtype=np.int64)
+    n_neg = 0
+    for u in range(g['y'].shape[0]):
+        x = torch.from_numpy(rs.rand(batch, 3, 32, 32).astype(np.float32))
+        rs.randint(0, 3, batch)                            # the generator drew the labels from the same stream
+        y = torch.from_numpy(g['y'][u])
+        torch.manual_seed(int(g['torch_seed0']) + u)
+        for pos, slot in ogss.update(st, x, y):
+            src[slot] = (u, pos)
+        np.testing.assert_array_equal(st.buffer_label.numpy(), g['labels'][u], err_msg='update %d' % u)
+        np.testing.assert_array_equal(src, g['src'][u], err_msg='update %d' % u)
+        np.testing.assert_allclose(st.buffer_score.numpy(), g['scores'][u], rtol=0, atol=1e-4)
+        if not np.isnan(g['batch_sim'][u]):
+            assert abs(st.last_batch_sim - float(g['batch_sim'][u])) <= 1e-4
+            n_neg += st.last_batch_sim < 0
+    assert n_neg == 2 and st.current_index == mem
