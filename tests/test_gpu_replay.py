@@ -293,3 +293,28 @@ def test_scr_augment_kernel(b):
     assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0 + 1e-6 and torch.isfinite(out).all()
     out2 = SCRTransform((32, 32))(x)                           # random parameters: shape / range only
     assert out2.shape == x.shape and torch.isfinite(out2).all()
+
+
+@pytest.mark.parametrize('hw,n,seed', [(32, 64, 0), (84, 12, 1), (32, 220, 2)])
+def test_scr_augment_kernel_vs_oracle(b, hw, n, seed):
+    """csrc/augment.cu with drawn parameters (crop boxes, flips, the four colour operations in every order, grayscale)
+    against oracle/augment.py (float64; itself checked against grid_sample and colorsys on the CPU).  kornia is absent:
+    the pipeline's definition is parity-unpinned, the kernel's arithmetic is not."""
+    from b200ocl.augment import SCRTransform, draw_params
+    from oracle import augment as oaug
+    rs = np.random.RandomState(seed)
+    x = rs.rand(n, 3, hw, hw).astype(np.float32)
+    x[0, :, :4, :4] = 0.5                                     # grey and black patches (hue undefined / value 0)
+    x[1, :, :4, :4] = 0.0
+    p = draw_params(n, hw, hw, rng=rs)
+    p[:, 5] = 1                                               # colour jitter on for every sample
+    for i in range(n):                                        # every sample its own operation order
+        order = rs.permutation(4)
+        p[i, 10] = float(sum(int(op) << (2 * k) for k, op in enumerate(order)))
+    p[::3, 5] = rs.rand(len(p[::3])) < 0.5
+    out = SCRTransform((hw, hw))(torch.from_numpy(x).cuda(), params=p).cpu().numpy()
+    ref = oaug.scr_view(x, p)
+    err = np.abs(out - ref)
+    assert err.max() <= 5e-5, (err.max(), np.unravel_index(err.argmax(), err.shape))
+    assert err.mean() <= 2e-7
+    assert (p[:, 2] < hw).any() and (p[:, 4] > 0.5).any() and (p[:, 11] > 0.5).any()     # the draws exercised crop / flip / gray
