@@ -229,7 +229,11 @@ def run_ours(args, rank, world):
     from b200ocl import engine as _engine
     _graphs_were = _engine._GRAPHS
     _engine.set_graphs(False)                 # the per-launch profiler needs eager launches (same kernels)
+    from b200ocl import learners as _learners
+    _conc_were = _learners._CONCURRENT
+    _learners.set_concurrent(False)           # ... on one stream: a class time must not contain another stream's kernels
     prof = profile_step(lambda i: step(i, False), args.warmup + args.steps - 1) if world == 1 else None
+    _learners.set_concurrent(_conc_were)
     _engine.set_graphs(_graphs_were)
     pk = peaks()
     line = {

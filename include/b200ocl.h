@@ -201,12 +201,22 @@ int b200ocl_net_forward_train(const b200ocl_net_desc* desc, const b200ocl_net_st
 int b200ocl_net_forward_evalgrad(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
                                  float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Train-mode forward with DEFERRED running statistics: identical outputs and saved activations, but the BatchNorm running
+ * statistics (and num_batches_tracked) are not touched; the batch statistics of every BN stay in `workspace` until
+ * b200ocl_net_apply_running_stats applies them (running = 0.9 running + 0.1 batch, tracked += 1).  The train-mode passes of
+ * one replay step (exp_replay.py:40,62,84; scr.py:55) only interact through those statistics, so a caller may run them
+ * concurrently on different streams and then apply their statistics in the reference's order. */
+int b200ocl_net_forward_train_deferred(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
+                                       float* out, void* workspace, size_t workspace_bytes, void* stream);
+int b200ocl_net_apply_running_stats(const b200ocl_net_desc* desc, const b200ocl_net_state* st, int N, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
 /* loss.backward() for the forward kept in `workspace` (same x): dout [N,out_dim] -> st->grads
  * (overwritten, or added to when accumulate != 0 -- exp_replay.py:55,77 accumulate two
  * backward passes before one opt.step()).  accumulate bit 1 (value 2): the forward was b200ocl_net_forward_evalgrad.
  * The weight-gradient launches run on a helper stream that is forked from / joined into `stream` with events (captured
- * as parallel branches when `stream` is being captured into a CUDA graph); the helper stream and its four events are the
- * one piece of per-device state the library creates itself, on the first call (B200OCL_WG_ASYNC=0: everything on `stream`). */
+ * as parallel branches when `stream` is being captured into a CUDA graph); the helper stream and its four events (one set per
+ * caller stream, at most four caller streams per device) are the one piece of state the library creates itself, on the first call (B200OCL_WG_ASYNC=0: everything on `stream`). */
 int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, const float* dout,
                          int N, void* workspace, size_t workspace_bytes, int accumulate, void* stream);
 

@@ -41,6 +41,8 @@ SIGNATURES = {
     'b200ocl_net_train_workspace_bytes': (c_size_t, [P, c_int]),
     'b200ocl_net_forward_train': (c_int, [P, P, P, c_int, P, P, c_size_t, P]),
     'b200ocl_net_forward_evalgrad': (c_int, [P, P, P, c_int, P, P, c_size_t, P]),
+    'b200ocl_net_forward_train_deferred': (c_int, [P, P, P, c_int, P, P, c_size_t, P]),
+    'b200ocl_net_apply_running_stats': (c_int, [P, P, c_int, P, c_size_t, P]),
     'b200ocl_net_backward': (c_int, [P, P, P, P, c_int, P, c_size_t, c_int, P]),
     'b200ocl_net_sgd_step': (c_int, [P, P, c_float, c_float, P, P]),
     'b200ocl_ce_loss': (c_int, [P, P, c_int, c_int, P, P, P, P, P]),

@@ -762,32 +762,50 @@ int linear_backward(const LinL& l, const float* params, float* grads, const floa
 // GPU (0.02-0.7 waves, profiles/r02_wgrad_ncu.md).  So wgrad(i) is launched on a side stream, forked after the
 // BN-backward that produced its dz and joined before the finalize; dz alternates between two buffers so that the next
 // BN-backward does not wait for it.  Fork / join are events, captured as parallel branches when the call is recorded
-// into a CUDA graph.  One side stream and four events per device, created on first (eager) use.
+// into a CUDA graph.  One side stream and four events per caller stream (bwd_async below), created on first use.
 namespace b200ocl {
 namespace {
 struct BwdAsync {
   cudaStream_t side = nullptr;
+  cudaStream_t owner = nullptr;   // the caller stream this slot serves
   cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
-  int state = 0;   // 0 = not tried, 1 = usable, -1 = disabled / failed
+  int state = 0;   // 0 = free, 1 = usable, -1 = failed
 };
-BwdAsync* bwd_async() {
-  static BwdAsync per_dev[B200OCL_MAX_DEVICES];
-  BwdAsync& a = per_dev[device_slot()];
-  if (a.state == 0) {
+constexpr int BWD_ASYNC_SLOTS = 4;
+// One helper stream + four events per CALLER STREAM (up to four caller streams per device): two backward passes that the
+// host runs concurrently on different streams (learners: SCR's two views) must not share fork / join events.  A fifth
+// caller stream gets no helper (serial weight gradients).  Slots are created on the first eager call from a stream; calls
+// recorded into CUDA graphs only need the events while capturing.
+BwdAsync* bwd_async(cudaStream_t caller) {
+  static BwdAsync per_dev[B200OCL_MAX_DEVICES][BWD_ASYNC_SLOTS];
+  static int enabled = -1;
+  if (enabled < 0) {
     const char* e = getenv("B200OCL_WG_ASYNC");
-    a.state = -1;
-    if (!(e && e[0] == '0')) {
-      int lo = 0, hi = 0;
-      cudaDeviceGetStreamPriorityRange(&lo, &hi);      // lo = least priority
-      bool ok = cudaStreamCreateWithPriority(&a.side, cudaStreamNonBlocking, lo) == cudaSuccess;
-      for (int i = 0; ok && i < 2; ++i)
-        ok = cudaEventCreateWithFlags(&a.ready[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&a.done[i], cudaEventDisableTiming) == cudaSuccess;
-      if (ok) a.state = 1;
-      else (void)cudaGetLastError();
-    }
+    enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  return a.state == 1 ? &a : nullptr;
+  if (!enabled) return nullptr;
+  BwdAsync* slots = per_dev[device_slot()];
+  for (int i = 0; i < BWD_ASYNC_SLOTS; ++i)
+    if (slots[i].state == 1 && slots[i].owner == caller) return &slots[i];
+  for (int i = 0; i < BWD_ASYNC_SLOTS; ++i) {
+    BwdAsync& a = slots[i];
+    if (a.state != 0) continue;
+    a.state = -1;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);      // lo = least priority
+    bool ok = cudaStreamCreateWithPriority(&a.side, cudaStreamNonBlocking, lo) == cudaSuccess;
+    for (int j = 0; ok && j < 2; ++j)
+      ok = cudaEventCreateWithFlags(&a.ready[j], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&a.done[j], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    a.owner = caller;
+    a.state = 1;
+    return &a;
+  }
+  return nullptr;
 }
 }  // namespace
 }  // namespace b200ocl
@@ -931,7 +949,7 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
   };
 
   // dz double buffer + fork / join (see bwd_async above)
-  BwdAsync* as = g_prof_on ? nullptr : bwd_async();   // per-launch profiling (bench.py) wants serial launches
+  BwdAsync* as = g_prof_on ? nullptr : bwd_async(stream);   // per-launch profiling (bench.py) wants serial launches
   float* dzbuf[2] = {w.g2, w.g4};
   bool pending[2] = {false, false};
   int cur = 0;

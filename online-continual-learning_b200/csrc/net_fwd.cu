@@ -479,8 +479,18 @@ __global__ void bn_save_running_kernel(const float* __restrict__ rmean, const fl
   }
 }
 
+// stats: where the BatchNorm statistics of a train-mode convolution go.
+//   STATS_RUNNING  the reference's train mode: batch statistics normalise, the running statistics move (momentum 0.1)
+//   STATS_EVAL     GSS-greedy's differentiable eval-mode pass: the running statistics normalise, nothing moves
+//   STATS_DEFER    batch statistics normalise; the running statistics are NOT touched: the (mean, unbiased variance) pair
+//                  of every BN is left in the workspace (momentum 1 into a zeroed buffer: 0 * 0 + 1 * s = s exactly) and
+//                  applied later, in the caller's order, by b200ocl_net_apply_running_stats -- so that several train-mode
+//                  passes of one step (exp_replay.py:40,62,84; scr.py:55) can run concurrently on different streams
+enum { STATS_RUNNING = 0, STATS_EVAL = 1, STATS_DEFER = 2 };
+
 int conv_train(const NetPlan& p, const b200ocl_net_state& st, const TrainWs& w, int ci, int N, const float* in,
-               cudaStream_t stream, bool eval_stats = false) {
+               cudaStream_t stream, int stats = STATS_RUNNING) {
+  const bool eval_stats = stats == STATS_EVAL;
   ConvArgs a;
   const ConvL& c = p.conv[ci];
   fill_conv_common(a, c, N, in, st.packed, w.z + (size_t)N * c.act_off);
@@ -492,6 +502,11 @@ int conv_train(const NetPlan& p, const b200ocl_net_state& st, const TrainWs& w, 
   a.save_invstd = w.save + b.save_off + b.c;
   a.run_mean = eval_stats ? w.run_scratch : st.bn_stats + b.stat_off;
   a.run_var = eval_stats ? w.run_scratch + 1024 : st.bn_stats + b.stat_off + b.c;
+  if (stats == STATS_DEFER) {
+    a.run_mean = w.run_defer + b.stat_off;
+    a.run_var = w.run_defer + b.stat_off + b.c;
+    a.momentum = 1.0f;
+  }
   const int rc = ci == 0 ? launch_stem(a, stream) : launch_conv(a, stream);
   if (rc == 0 && eval_stats) {
     bn_save_running_kernel<<<(b.c + 127) / 128, 128, 0, stream>>>(st.bn_stats + b.stat_off, st.bn_stats + b.stat_off + b.c, a.eps,
@@ -560,6 +575,15 @@ int head_forward(const NetPlan& p, const b200ocl_net_state& st, const float* fea
   l2norm_fwd_kernel<<<(N + 7) / 8, 256, 0, stream>>>(pre, out, N, p.out_dim);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
+}
+
+// running = (1 - momentum) * running + momentum * s for every BN statistic (the expression the convolution epilogues
+// use), plus num_batches_tracked += 1: one deferred train-mode pass applied to the running statistics
+__global__ void bn_running_apply_kernel(float* __restrict__ run, const float* __restrict__ s, int n, float momentum,
+                                        long long* __restrict__ tracked, int n_bn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) run[i] = (1.f - momentum) * run[i] + momentum * s[i];
+  if (tracked && i < n_bn) tracked[i] += 1;
 }
 
 __global__ void bump_tracked_kernel(long long* t, int n) {
@@ -799,7 +823,7 @@ size_t b200ocl_net_train_workspace_bytes(const b200ocl_net_desc* desc, int N) {
 }
 
 static int net_forward_impl(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N, float* out,
-                            void* workspace, size_t workspace_bytes, void* stream_, bool ev) {
+                            void* workspace, size_t workspace_bytes, void* stream_, int ev) {
   using namespace b200ocl;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NetPlan p;
@@ -813,6 +837,7 @@ static int net_forward_impl(const b200ocl_net_desc* desc, const b200ocl_net_stat
   }
   TrainWs w = train_ws(p, N, workspace, sm_count());
   B200OCL_CUDA(cudaMemsetAsync(w.counters, 0, NET_COUNTERS * sizeof(unsigned int), stream));
+  if (ev == STATS_DEFER) B200OCL_CUDA(cudaMemsetAsync(w.run_defer, 0, p.n_stats * sizeof(float), stream));
   if ((rc = conv_train(p, *st, w, 0, N, x, stream, ev))) return rc;
   if ((rc = bn_apply_train(p, *st, w, 0, N, -1, nullptr, stream))) return rc;
   const float* cur = w.a + (size_t)N * p.conv[0].act_off;
@@ -830,7 +855,7 @@ static int net_forward_impl(const b200ocl_net_desc* desc, const b200ocl_net_stat
     }
     cur = w.a + (size_t)N * p.conv[B.c2].act_off;
   }
-  if (st->bn_tracked && !ev) {
+  if (st->bn_tracked && ev == STATS_RUNNING) {
     B200OCL_PROF("misc", 16.0 * p.n_conv, stream);
     bump_tracked_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<long long*>(st->bn_tracked), p.n_conv);
     B200OCL_LAUNCHED();
@@ -845,12 +870,39 @@ static int net_forward_impl(const b200ocl_net_desc* desc, const b200ocl_net_stat
 
 int b200ocl_net_forward_train(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
                               float* out, void* workspace, size_t workspace_bytes, void* stream_) {
-  return net_forward_impl(desc, st, x, N, out, workspace, workspace_bytes, stream_, false);
+  return net_forward_impl(desc, st, x, N, out, workspace, workspace_bytes, stream_, b200ocl::STATS_RUNNING);
 }
 
 int b200ocl_net_forward_evalgrad(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
                                  float* out, void* workspace, size_t workspace_bytes, void* stream_) {
-  return net_forward_impl(desc, st, x, N, out, workspace, workspace_bytes, stream_, true);
+  return net_forward_impl(desc, st, x, N, out, workspace, workspace_bytes, stream_, b200ocl::STATS_EVAL);
+}
+
+int b200ocl_net_forward_train_deferred(const b200ocl_net_desc* desc, const b200ocl_net_state* st, const float* x, int N,
+                                       float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  return net_forward_impl(desc, st, x, N, out, workspace, workspace_bytes, stream_, b200ocl::STATS_DEFER);
+}
+
+int b200ocl_net_apply_running_stats(const b200ocl_net_desc* desc, const b200ocl_net_state* st, int N, void* workspace,
+                                    size_t workspace_bytes, void* stream_) {
+  using namespace b200ocl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NetPlan p;
+  int rc = check_state(desc, st, p);
+  if (rc) return rc;
+  B200OCL_CHECK_ARG(N >= 1, "need N >= 1");
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) ||
+      workspace_bytes < b200ocl_net_train_workspace_bytes(desc, N)) {
+    set_error("b200ocl_net_apply_running_stats: workspace missing, misaligned or too small");
+    return B200OCL_EWORKSPACE;
+  }
+  TrainWs w = train_ws(p, N, workspace, sm_count());
+  const int n = (int)p.n_stats;
+  B200OCL_PROF("misc", 12.0 * n, stream);
+  bn_running_apply_kernel<<<(n + 255) / 256, 256, 0, stream>>>(st->bn_stats, w.run_defer, n, NET_BN_MOMENTUM,
+                                                               reinterpret_cast<long long*>(st->bn_tracked), p.n_conv);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
 }
 
 int b200ocl_ce_loss(const float* logits, const int64_t* labels, int N, int C, float* loss, float* per_sample,

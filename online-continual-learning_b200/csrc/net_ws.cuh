@@ -86,6 +86,7 @@ struct TrainWs {
   double* stat_part;
   float* save;    // batch mean / invstd per BN (BnL::save_off)
   float* run_scratch;  // [2][1024] throw-away running statistics (eval-statistics forward, net_fwd.cu)
+  float* run_defer;    // deferred-statistics forward: (batch mean, unbiased batch variance) per BN, laid out like bn_stats
   float* z;       // raw conv outputs, conv i at N * ConvL::act_off
   float* a;       // activated outputs (conv2 slot holds the block output)
   float* feat;    // [N, dim_in]
@@ -126,6 +127,7 @@ inline TrainWs train_ws(const NetPlan& p, int N, void* base, int sms) {
   w.stat_part = reinterpret_cast<double*>(take(stat_max));
   w.save = reinterpret_cast<float*>(take(2 * p.n_bn_channels * sizeof(float)));
   w.run_scratch = reinterpret_cast<float*>(take(2 * 1024 * sizeof(float)));
+  w.run_defer = reinterpret_cast<float*>(take(p.n_stats * sizeof(float)));
   w.z = reinterpret_cast<float*>(take((size_t)N * p.act_per_image * sizeof(float)));
   w.a = reinterpret_cast<float*>(take((size_t)N * p.act_per_image * sizeof(float)));
   w.feat = reinterpret_cast<float*>(take((size_t)N * p.dim_in * sizeof(float)));

@@ -230,27 +230,32 @@ class Engine:
                 self._train_ws[key] = ws
         return ws
 
-    def forward_train(self, x, ws=None, state=None, slot=0, eval_stats=False):
+    def forward_train(self, x, ws=None, state=None, slot=0, eval_stats=False, defer_stats=False):
         """model.train(); model.forward(x).  Returns (out [N,out_dim], workspace kept for backward).
-        eval_stats=True: model.eval() forward that can be differentiated (running statistics, nothing updated)."""
+        eval_stats=True: model.eval() forward that can be differentiated (running statistics, nothing updated).
+        defer_stats=True: the BN running statistics are left alone; apply_running_stats(ws, N) moves them later (so that
+        the train-mode passes of one step can run concurrently on different streams and still update the statistics in
+        the reference's order)."""
         x = self._x(x)
         n = x.shape[0]
         graphed = _GRAPHS and ws is None and state is None and (n, slot) in self._train_ws and not eval_stats
         if ws is None:
             ws = self.train_workspace(n, slot)
         st = state or self.state
+        name = ('b200ocl_net_forward_evalgrad' if eval_stats else
+                'b200ocl_net_forward_train_deferred' if defer_stats else 'b200ocl_net_forward_train')
 
         def launch(xin, out):
-            fn = _lib().b200ocl_net_forward_evalgrad if eval_stats else _lib().b200ocl_net_forward_train
-            rc = fn(ctypes.byref(self.desc), ctypes.byref(st.c), xin.data_ptr(), n, out.data_ptr(), ws.data_ptr(), ws.numel(),
-                    _stream())
-            _native.check(rc, 'b200ocl_net_forward_evalgrad' if eval_stats else 'b200ocl_net_forward_train')
+            rc = getattr(_lib(), name)(ctypes.byref(self.desc), ctypes.byref(st.c), xin.data_ptr(), n, out.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), _stream())
+            _native.check(rc, name)
 
         if graphed:
-            key = ('fwd', n, slot)
+            key = ('fwd', n, slot, bool(defer_stats))
             e = self._graphs.get(key)
             if e is None:
-                e = self._graphs[key] = _Graphed([torch.empty_like(x)],
+                other = self._graphs.get(('fwd', n, slot, not defer_stats))     # one static input per (n, slot)
+                e = self._graphs[key] = _Graphed([other.inputs[0] if other is not None else torch.empty_like(x)],
                                                  [torch.empty((n, self.out_dim), dtype=torch.float32, device=x.device)])
             e.inputs[0].copy_(x)
             e.run(lambda: launch(e.inputs[0], e.outputs[0]))
@@ -259,27 +264,52 @@ class Engine:
         launch(x, out)
         return out, ws
 
-    def backward(self, x, dout, ws, accumulate=False, eval_stats=False):
+    def apply_running_stats(self, ws, n):
+        """The running-statistics update of a forward_train(..., defer_stats=True) over n images kept in ws."""
+        rc = _lib().b200ocl_net_apply_running_stats(ctypes.byref(self.desc), ctypes.byref(self.state.c), int(n), ws.data_ptr(),
+                                                    ws.numel(), _stream())
+        _native.check(rc, 'b200ocl_net_apply_running_stats')
+
+    def alt_grads(self):
+        """A second gradient arena (same layout): a backward pass that runs concurrently with another one writes here,
+        add_alt_grads() folds it into the arena the optimizer reads."""
+        if getattr(self, '_alt', None) is None:
+            g = torch.zeros_like(self.state.grads)
+            c = NetState(self.state.params.data_ptr(), g.data_ptr(), self.state.packed.data_ptr(),
+                         self.state.bn_stats.data_ptr(), self.state.bn_tracked.data_ptr())
+            self._alt = (g, c)
+        return self._alt[0]
+
+    def add_alt_grads(self):
+        """grads += alt (one rounding per element: the same sum an accumulating backward pass forms)."""
+        g, alt = self.state.grads, self.alt_grads()
+        rc = _lib().b200ocl_sgd_step(g.data_ptr(), alt.data_ptr(), g.data_ptr(), g.numel(), -1.0, 0.0, _stream())
+        _native.check(rc, 'b200ocl_sgd_step')
+
+    def backward(self, x, dout, ws, accumulate=False, eval_stats=False, alt=False):
         """loss.backward() for the forward of the same x kept in ws; fills (or adds to) the grad arena.
-        eval_stats=True: the forward was forward_train(..., eval_stats=True)."""
+        eval_stats=True: the forward was forward_train(..., eval_stats=True).  alt=True: into the second arena."""
         _need_cuda(dout)
         x = self._x(x)
         dout = dout.detach().to(torch.float32).contiguous()
         n = dout.shape[0]
         if x.shape[0] != n or dout.shape[1] != self.out_dim:
             raise ValueError('dout must be [N, out_dim] for the same N as x')
+        if alt:
+            self.alt_grads()
+        st_c = self._alt[1] if alt else self.state.c
 
         def launch(xin, din):
-            rc = _lib().b200ocl_net_backward(ctypes.byref(self.desc), ctypes.byref(self.state.c), xin.data_ptr(),
+            rc = _lib().b200ocl_net_backward(ctypes.byref(self.desc), ctypes.byref(st_c), xin.data_ptr(),
                                              din.data_ptr(), n, ws.data_ptr(), ws.numel(),
                                              (1 if accumulate else 0) | (2 if eval_stats else 0), _stream())
             _native.check(rc, 'b200ocl_net_backward')
 
         slot = next((k[1] for k, w in self._train_ws.items() if w is ws and k[0] == n), None) if (_GRAPHS and not eval_stats) else None
-        fwd = self._graphs.get(('fwd', n, slot)) if slot is not None else None
+        fwd = (self._graphs.get(('fwd', n, slot, False)) or self._graphs.get(('fwd', n, slot, True))) if slot is not None else None
         if fwd is not None:
             # the images are the static copy the graphed forward read (same data as x)
-            key = ('bwd', n, slot, bool(accumulate))
+            key = ('bwd', n, slot, bool(accumulate), bool(alt))
             e = self._graphs.get(key)
             if e is None:
                 e = self._graphs[key] = _Graphed([fwd.inputs[0], torch.empty_like(dout)], [])

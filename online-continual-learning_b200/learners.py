@@ -19,6 +19,21 @@ from .memory import Buffer, input_size_match
 from .nets import adopt, engine_of, EngineModel
 
 
+# The train-mode passes of one replay step only interact through the BatchNorm running statistics and the gradient arena.
+# With this switch on (default; B200OCL_CONCURRENT=0 turns it off) independent passes are issued on two streams -- SCR's two
+# views (forward and backward), the memory / combined forwards of the ASER branch -- with deferred statistics applied in the
+# reference's order and the second backward pass into a second gradient arena.  Measured on one B200: two N=110 passes
+# 5.00 -> 3.91 ms, two N=10 forwards 0.76 -> 0.45 ms (tools/overlap_probe.py): most launches of this network fill a
+# fraction of the GPU.
+import os as _os
+_CONCURRENT = _os.environ.get('B200OCL_CONCURRENT', '1') != '0'
+
+
+def set_concurrent(on):
+    global _CONCURRENT
+    _CONCURRENT = bool(on)
+
+
 class AverageMeter(object):
     """utils/utils.py:25-42, but values may stay on the device until avg() is read."""
 
@@ -106,6 +121,15 @@ class ContinualLearner(torch.nn.Module):
         self.device = self.engine.device
         self.grad_sync = None      # data-parallel stream shards: callable(engine) summing gradients over ranks
         self.grad_world = 1
+
+    def _fork(self):
+        """(main, side) streams with side ordered after everything issued on main so far."""
+        main = torch.cuda.current_stream()
+        side = self.__dict__.get('_side_stream')
+        if side is None:
+            side = self.__dict__['_side_stream'] = torch.cuda.Stream(device=self.device)
+        side.wait_stream(main)
+        return main, side
 
     def _throttle(self, depth=2):
         """Keep the host at most `depth` replay steps ahead of the GPU: the stream never runs dry, the launch
@@ -276,9 +300,19 @@ class ExperienceReplay(ContinualLearner):
             if self._needs_batch_grad:
                 eng.backward(batch_x, ce['dlogits'], ws)                            # :54-55
             mem_x, mem_y = self.buffer.retrieve(x=batch_x, y=batch_y)               # :58
-            if mem_x.size(0) > 0:
+            both = _CONCURRENT and aser and mem_x.size(0) > 0
+            if both:
+                # ASER branch: the memory forward (:62, kept for its BN side effect and the meters) and the forward of the
+                # concatenated batch (:84) are independent -- two streams, statistics applied in call order
+                main, side = self._fork()
+                with torch.cuda.stream(side):
+                    mem_logits, ws_m = eng.forward_train(mem_x, slot=1, defer_stats=True)
+                    if meters is not None:
+                        ce_m = ce_loss(mem_logits, mem_y, want_grad=False, want_correct=True)
+            elif mem_x.size(0) > 0:
                 mem_logits, ws_m = eng.forward_train(mem_x, slot=1)                 # :62  (BN stats move)
                 ce_m = ce_loss(mem_logits, mem_y, want_grad=not aser, want_correct=meters is not None)
+            if mem_x.size(0) > 0 and not both:
                 if meters is not None:
                     meters['losses_mem'].update(ce_m['loss'], mem_y.size(0))
                     meters['acc_mem'].update(ce_m['n_correct'] / mem_y.size(0), mem_y.size(0))
@@ -287,7 +321,14 @@ class ExperienceReplay(ContinualLearner):
             if aser:
                 combined = torch.cat((mem_x, batch_x))                              # :82-83
                 labels = torch.cat((mem_y, batch_y))
-                logits_c, ws_c = eng.forward_train(combined, slot=3)                # :84
+                logits_c, ws_c = eng.forward_train(combined, slot=3, defer_stats=both)   # :84
+                if both:
+                    main.wait_stream(side)
+                    eng.apply_running_stats(ws_m, mem_x.size(0))
+                    eng.apply_running_stats(ws_c, combined.size(0))
+                    if meters is not None:
+                        meters['losses_mem'].update(ce_m['loss'], mem_y.size(0))
+                        meters['acc_mem'].update(ce_m['n_correct'] / mem_y.size(0), mem_y.size(0))
                 ce_c = ce_loss(logits_c, labels, want_grad=True)
                 eng.backward(combined, ce_c['dlogits'], ws_c)                       # :86
                 self.last_loss = ce_c['loss']
@@ -334,12 +375,31 @@ class SupContrastReplay(ContinualLearner):
                 combined = torch.cat((mem_x, batch_x))                              # :52-53
                 labels = torch.cat((mem_y, batch_y))
                 combined_aug = self.transform(combined)                             # :54
-                f1, ws1 = eng.forward_train(combined, slot=0)                       # :55 two train-mode forwards
-                f2, ws2 = eng.forward_train(combined_aug, slot=1)
-                feats = torch.stack((f1, f2), dim=1)
-                loss, dfeat = ops.supcon(feats, labels, self.params.temp)           # :56  (base.py:109-111)
-                eng.backward(combined, dfeat[:, 0].contiguous(), ws1)               # :58-59
-                eng.backward(combined_aug, dfeat[:, 1].contiguous(), ws2, accumulate=True)
+                if _CONCURRENT:
+                    n = combined.size(0)
+                    main, side = self._fork()
+                    with torch.cuda.stream(side):                                   # :55 two train-mode forwards, side by side
+                        f2, ws2 = eng.forward_train(combined_aug, slot=1, defer_stats=True)
+                    f1, ws1 = eng.forward_train(combined, slot=0, defer_stats=True)
+                    main.wait_stream(side)
+                    eng.apply_running_stats(ws1, n)                                 # the running statistics move in call order
+                    eng.apply_running_stats(ws2, n)
+                    feats = torch.stack((f1, f2), dim=1)
+                    loss, dfeat = ops.supcon(feats, labels, self.params.temp)       # :56  (base.py:109-111)
+                    d1, d2 = dfeat[:, 0].contiguous(), dfeat[:, 1].contiguous()
+                    main, side = self._fork()
+                    with torch.cuda.stream(side):                                   # :58-59 one backward per view
+                        eng.backward(combined_aug, d2, ws2, alt=True)
+                    eng.backward(combined, d1, ws1)
+                    main.wait_stream(side)
+                    eng.add_alt_grads()
+                else:
+                    f1, ws1 = eng.forward_train(combined, slot=0)                   # :55 two train-mode forwards
+                    f2, ws2 = eng.forward_train(combined_aug, slot=1)
+                    feats = torch.stack((f1, f2), dim=1)
+                    loss, dfeat = ops.supcon(feats, labels, self.params.temp)       # :56  (base.py:109-111)
+                    eng.backward(combined, dfeat[:, 0].contiguous(), ws1)           # :58-59
+                    eng.backward(combined_aug, dfeat[:, 1].contiguous(), ws2, accumulate=True)
                 self._optimizer_step(lr, wd)                                        # :60
                 self.last_loss = loss
                 if meters is not None:

@@ -287,3 +287,45 @@ def test_train_step_matches_oracle(eng_mod):
         eng.sgd_step(0.1)
     flat = torch.cat([v.reshape(-1) for v in params.values()])
     assert rel_err(eng.state.params.cpu().numpy(), flat.numpy()) < 5e-2    # free-running, chaotic (see above)
+
+
+@pytest.mark.parametrize('head,N', [(None, 10), ('mlp', 110)])
+def test_deferred_statistics_and_second_arena(eng_mod, head, N):
+    """The concurrent form of a step (learners._CONCURRENT): two train-mode passes on two streams with deferred running
+    statistics + a second gradient arena give what the sequential form gives -- outputs and gradients bit for bit,
+    running statistics to one rounding, num_batches_tracked exactly."""
+    spec = oresnet.Spec(32, 20, 100, head=head)
+    outs = {}
+    for mode in ('sequential', 'concurrent'):
+        eng, params, bn = make_engine(eng_mod, spec, 41)
+        gen = torch.Generator().manual_seed(5)
+        x1, x2 = torch.rand(N, 3, 32, 32, generator=gen).cuda(), torch.rand(N, 3, 32, 32, generator=gen).cuda()
+        d1, d2 = torch.randn(N, eng.out_dim, generator=gen).cuda(), torch.randn(N, eng.out_dim, generator=gen).cuda()
+        for rep in range(3):                                   # eager call, graph capture, graph replay
+            if mode == 'sequential':
+                o1, w1 = eng.forward_train(x1, slot=0)
+                o2, w2 = eng.forward_train(x2, slot=1)
+                eng.backward(x1, d1, w1)
+                eng.backward(x2, d2, w2, accumulate=True)
+            else:
+                main, side = torch.cuda.current_stream(), torch.cuda.Stream()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    o2, w2 = eng.forward_train(x2, slot=1, defer_stats=True)
+                o1, w1 = eng.forward_train(x1, slot=0, defer_stats=True)
+                main.wait_stream(side)
+                eng.apply_running_stats(w1, N)
+                eng.apply_running_stats(w2, N)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    eng.backward(x2, d2, w2, alt=True)
+                eng.backward(x1, d1, w1)
+                main.wait_stream(side)
+                eng.add_alt_grads()
+            torch.cuda.synchronize()
+        outs[mode] = (o1.cpu(), o2.cpu(), eng.state.grads.cpu(), eng.state.bn_stats.cpu(), eng.state.bn_tracked.cpu())
+    s, c = outs['sequential'], outs['concurrent']
+    assert torch.equal(s[0], c[0]) and torch.equal(s[1], c[1])
+    assert torch.equal(s[2], c[2]), float((s[2] - c[2]).abs().max())
+    torch.testing.assert_close(c[3], s[3], rtol=3e-7, atol=1e-9)
+    assert torch.equal(s[4], c[4]) and int(s[4][0]) == 6

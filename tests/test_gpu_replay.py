@@ -316,5 +316,5 @@ def test_scr_augment_kernel_vs_oracle(b, hw, n, seed):
     ref = oaug.scr_view(x, p)
     err = np.abs(out - ref)
     assert err.max() <= 5e-5, (err.max(), np.unravel_index(err.argmax(), err.shape))
-    assert err.mean() <= 2e-7
+    assert err.mean() <= (2e-7 if hw <= 32 else 3e-6)     # fp32 sampling coordinates: ulp(83) = 7.6e-6 pixels on noise images
     assert (p[:, 2] < hw).any() and (p[:, 4] > 0.5).any() and (p[:, 11] > 0.5).any()     # the draws exercised crop / flip / gray
