@@ -335,6 +335,10 @@ class ExperienceReplay(ContinualLearner):
             else:
                 self.last_loss = ce['loss']
             self._optimizer_step(lr, wd)                                            # :87 / :89
+        # (Measured and dropped: issuing this update next to the FOLLOWING iteration's first forward on a second stream.
+        # The update's eval-feature pass runs persistent one-CTA-per-SM kernels, the forward cannot share the SMs with
+        # them: 1.40 ms for the pair against 0.96 + 0.41 ms one after the other, and the host then waits for the update's
+        # decision at the next retrieval.)
         self.buffer.update(batch_x, batch_y, y_host=batch_y_host)                   # :92
         self._throttle()
 

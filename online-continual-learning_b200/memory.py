@@ -120,12 +120,25 @@ class _PinnedRing:
     def _alloc(self, shape, dtype, device):
         return torch.empty(shape, dtype=dtype, device=device)
 
+    class _Events(list):
+        def synchronize(self):
+            for ev in self:
+                ev.synchronize()
+
     def _record(self):
-        ev = torch.cuda.Event()
-        ev.record()
-        return ev
+        """One event per stream that issued a copy out of the half being left (the learners issue work on two streams)."""
+        evs = self._Events()
+        for st in self.__dict__.pop('_streams', None) or [torch.cuda.current_stream()]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            evs.append(ev)
+        return evs
 
     def _copy(self, out, view):
+        streams = self.__dict__.setdefault('_streams', [])
+        cur = torch.cuda.current_stream()
+        if cur not in streams:
+            streams.append(cur)
         out.view(torch.uint8).reshape(-1).copy_(view, non_blocking=True)
 
     def reserve(self, n):

@@ -318,3 +318,41 @@ def test_scr_augment_kernel_vs_oracle(b, hw, n, seed):
     assert err.max() <= 5e-5, (err.max(), np.unravel_index(err.argmax(), err.shape))
     assert err.mean() <= (2e-7 if hw <= 32 else 3e-6)     # fp32 sampling coordinates: ulp(83) = 7.6e-6 pixels on noise images
     assert (p[:, 2] < hw).any() and (p[:, 4] > 0.5).any() and (p[:, 11] > 0.5).any()     # the draws exercised crop / flip / gray
+
+
+@pytest.mark.parametrize('kind', ['aser', 'scr'])
+def test_concurrent_step_equals_sequential_step(b, kind):
+    """learners._CONCURRENT (two streams, deferred running statistics, second gradient arena) against the plain sequential step: same memory, same random draws, weights bit
+    for bit, running statistics to rounding."""
+    from b200ocl import learners
+    res = {}
+    for mode in (False, True):
+        learners.set_concurrent(mode)
+        try:
+            kw = dict(retrieve='ASER', update='ASER', n_smp_cls=1) if kind == 'aser' else \
+                dict(agent='SCR', eps_mem_batch=20, data='cifar100', mem_size=60)
+            b.memory.ClassBalancedRandomSampling.reset()
+            params, agent, st = _agent_and_oracle(b, 260, 10 if kind == 'aser' else 100, **kw)
+            if kind == 'scr':
+                from b200ocl.augment import Identity
+                agent.transform = Identity()
+            agent.model.train()
+            np.random.seed(77); torch.manual_seed(77)
+            for i, (x, y) in enumerate(_batches(12, 9, 4)):
+                agent.replay_step(x.cuda(), y.cuda(), y.numpy())
+            torch.cuda.synchronize()
+            res[mode] = (agent.engine.state.params.cpu(), agent.engine.state.bn_stats.cpu(), agent.buffer.buffer_label.cpu(),
+                         agent.buffer.buffer_img.cpu(), agent.buffer.labels_host.copy(), np.random.get_state()[1].copy(),
+                         torch.get_rng_state().clone(), agent.engine.state.bn_tracked.cpu())
+        finally:
+            learners.set_concurrent(True)
+    s, c = res[False], res[True]
+    assert torch.equal(s[2], c[2]) and torch.equal(s[3], c[3]) and np.array_equal(s[4], c[4])
+    assert np.array_equal(s[5], c[5]) and torch.equal(s[6], c[6]) and torch.equal(s[7], c[7])
+    torch.testing.assert_close(c[1], s[1], rtol=1e-6, atol=1e-9)
+    if kind == 'scr':
+        assert torch.equal(s[0], c[0])                       # train-mode arithmetic does not read the running statistics
+    else:
+        # ASER's eval features read them: a one-rounding difference may reach the weights through a different retrieval
+        # only at an exact score tie; the memory is identical above, so the weights are too
+        assert torch.equal(s[0], c[0])
