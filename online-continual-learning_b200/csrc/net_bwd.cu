@@ -892,6 +892,18 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
   };
   auto wgrad_on = [&](int ci, const float* x, const float* dz, cudaStream_t stream) -> int {
     const ConvL& c = p.conv[ci];
+    {
+      // 3x3 stride-1 layers on 4..32-wide maps: tcgen05 with both operands read in place from strips (wgrad_tc.cu)
+      const WgradTcCfg tg = wgrad_tc_cfg(N, c.hin, c.win, c.ks, c.stride, c.pad, c.cin, c.cout, sms);
+      if (tg.eligible && wgrad_tc_enabled()) {
+        WgradTcArgs ta{};
+        ta.x = x; ta.dz = dz;
+        ta.part = w.wg_part + w.wg_off[ci];
+        ta.N = N; ta.H = c.hin; ta.W = c.win; ta.Cin = c.cin; ta.Cout = c.cout;
+        ta.tpc = tg.tpc; ta.chains = tg.chains; ta.chains_per_cta = tg.chains_per_cta;
+        return launch_wgrad_tc(ta, tg, stream);
+      }
+    }
     const WgradCfg g = wgrad_cfg(c, N, sms);
     WgradArgs a{};
     a.x = x; a.dz = dz;
@@ -1030,6 +1042,11 @@ extern "C" int b200ocl_net_backward(const b200ocl_net_desc* desc, const b200ocl_
       e.cout = p.conv[i].cout;
       e.taps = p.conv[i].ks * p.conv[i].ks;
       e.splits = (i == 0) ? grid : wgrad_cfg(p.conv[i], N, sms).splits;
+      if (i > 0 && wgrad_tc_enabled()) {
+        const ConvL& ci_ = p.conv[i];
+        const WgradTcCfg tg = wgrad_tc_cfg(N, ci_.hin, ci_.win, ci_.ks, ci_.stride, ci_.pad, ci_.cin, ci_.cout, sms);
+        if (tg.eligible) e.splits = tg.chains;
+      }
       e.sg_log2 = e.splits >= 256 ? 5 : (e.splits >= 64 ? 4 : (e.splits >= 16 ? 3 : 2));
       e.blk_start = blocks;
       const int epb = 256 >> e.sg_log2;

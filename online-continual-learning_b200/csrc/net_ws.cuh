@@ -1,5 +1,6 @@
 // net_ws.cuh -- carving of the caller-provided workspaces of the ResNet engine.
 #pragma once
+#include "wgrad_tc.cuh"
 #include <stdlib.h>
 #include "conv.cuh"
 #include "net_plan.cuh"
@@ -149,7 +150,10 @@ inline TrainWs train_ws(const NetPlan& p, int N, void* base, int sms) {
       wg += (size_t)(8 * sms) * 27 * 20;  // stem: one partial per CTA
     } else {
       const WgradCfg g = wgrad_cfg(p.conv[i], N, sms);
-      wg += (size_t)g.splits * g.k_total * p.conv[i].cout;
+      const ConvL& c = p.conv[i];
+      const WgradTcCfg tg = wgrad_tc_cfg(N, c.hin, c.win, c.ks, c.stride, c.pad, c.cin, c.cout, sms);   // wgrad_tc.cu
+      const int splits = (tg.eligible && tg.chains > g.splits) ? tg.chains : g.splits;
+      wg += (size_t)splits * g.k_total * p.conv[i].cout;
     }
   }
   w.wg_part = reinterpret_cast<float*>(take(wg * sizeof(float)));

@@ -167,8 +167,95 @@ __global__ void __launch_bounds__(128) umma_window_kernel(const float* __restric
   if (warp == 0) umma::tmem_dealloc(tmem, ncols);
 }
 
+// MN-major test: both operands are windows into "strips" of 128-byte rows (32 fp32 per row, stored with the 32-byte-base
+// swizzle keyed on the absolute row index, umma::sw128b32_offset_f32), the contraction runs over ROWS:
+//   D[32 j + c][32 q + n] = sum_{g < 2 ksteps} sum_{t < 4} PA[a_row0 + j a_lbo_rows + g a_sbo_rows + t][c]
+//                                                        * PB[b_row0 + q b_lbo_rows + g b_sbo_rows + t][n]
+// for the 4 M blocks j and the N / 32 N blocks q (consecutive K steps advance both windows by 2 * sbo rows).
+// a_lbo_rows = 1, a_sbo_rows = 4 is the weight-gradient case: M block j is the same strip shifted by j rows (the kernel
+// column kw of a 3x3 tap), K runs over 8 consecutive rows.
+__global__ void __launch_bounds__(128) umma_mn_kernel(const float* __restrict__ PA, const float* __restrict__ PB,
+                                                      float* __restrict__ D, int rows_a, int rows_b, int a_row0,
+                                                      int a_lbo_rows, int a_sbo_rows, int b_row0, int b_lbo_rows, int b_sbo_rows,
+                                                      int ksteps, int N, int* __restrict__ status) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* sA = reinterpret_cast<float*>(smem_raw);
+  float* sB = sA + (size_t)((rows_a + 7) / 8 * 8) * 32;
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_slot, ncols);
+  if (tid == 0) {
+    umma::mbar_init(&mbar, 1);
+    umma::fence_mbar_init();
+  }
+  for (int idx = tid; idx < rows_a * 8; idx += 128) {
+    const int r = idx >> 3, c = idx & 7;
+    *reinterpret_cast<float4*>(sA + umma::sw128b32_offset_f32(r, c)) = *reinterpret_cast<const float4*>(PA + (size_t)r * 32 + c * 4);
+  }
+  for (int idx = tid; idx < rows_b * 8; idx += 128) {
+    const int r = idx >> 3, c = idx & 7;
+    *reinterpret_cast<float4*>(sB + umma::sw128b32_offset_f32(r, c)) = *reinterpret_cast<const float4*>(PB + (size_t)r * 32 + c * 4);
+  }
+  umma::fence_proxy_async_smem();
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t idesc = umma::make_idesc_tf32_major(128, N, 1, 1);
+  if (tid == 0) {
+    const uint64_t dA = umma::make_smem_desc_mn_b32(umma::smem_u32(sA) + (uint32_t)a_row0 * 128u, (uint32_t)a_lbo_rows * 128u,
+                                                    (uint32_t)a_sbo_rows * 128u);
+    const uint64_t dB = umma::make_smem_desc_mn_b32(umma::smem_u32(sB) + (uint32_t)b_row0 * 128u, (uint32_t)b_lbo_rows * 128u,
+                                                    (uint32_t)b_sbo_rows * 128u);
+    for (int k = 0; k < ksteps; ++k) {
+      const uint64_t adv_a = (uint64_t)(k * 2 * a_sbo_rows * 128 >> 4), adv_b = (uint64_t)(k * 2 * b_sbo_rows * 128 >> 4);
+      umma::mma_tf32_ss(tmem, dA + adv_a, dB + adv_b, idesc, k > 0 ? 1u : 0u);
+    }
+    umma::mma_commit(&mbar);
+  }
+  const bool ok = umma::mbar_wait(&mbar, 0);
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  if (ok) {
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16];
+      umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) D[(size_t)row * N + c0 + j] = v[j];
+    }
+  }
+  if (tid == 0) *status = ok ? 0 : 1;
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
 }  // namespace
 }  // namespace b200ocl
+
+extern "C" int b200ocl_selftest_umma_mn(const float* PA, const float* PB, float* D, int rows_a, int rows_b, int a_row0,
+                                        int a_lbo_rows, int a_sbo_rows, int b_row0, int b_lbo_rows, int b_sbo_rows, int ksteps,
+                                        int N, int* status, void* stream_) {
+  using namespace b200ocl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200OCL_CHECK_ARG(PA && PB && D && status, "null pointer");
+  B200OCL_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && ksteps >= 1 && ksteps <= 64, "need N in [16,256] %16, 1 <= ksteps <= 64");
+  B200OCL_CHECK_ARG(rows_a > 0 && rows_b > 0 && rows_a + rows_b <= 1600 && a_row0 >= 0 && b_row0 >= 0 && a_lbo_rows >= 1 &&
+                        b_lbo_rows >= 1 && a_sbo_rows >= 1 && b_sbo_rows >= 1 &&
+                        a_row0 + 3 * a_lbo_rows + (2 * ksteps - 1) * a_sbo_rows + 4 <= rows_a &&
+                        b_row0 + ((N + 31) / 32 - 1) * b_lbo_rows + (2 * ksteps - 1) * b_sbo_rows + 4 <= rows_b,
+                    "window exceeds the strips");
+  const size_t smem = (size_t)((rows_a + 7) / 8 * 8 + (rows_b + 7) / 8 * 8) * 32 * sizeof(float) + 1024;
+  B200OCL_CUDA(cudaFuncSetAttribute(umma_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_mn_kernel<<<1, 128, smem, stream>>>(PA, PB, D, rows_a, rows_b, a_row0, a_lbo_rows, a_sbo_rows, b_row0, b_lbo_rows, b_sbo_rows,
+                                           ksteps, N, status);
+  B200OCL_LAUNCHED();
+  return B200OCL_OK;
+}
 
 extern "C" int b200ocl_selftest_umma_tf32(const float* A, const float* B, float* D, int N, int K, int mode, int* status,
                                           void* stream_) {

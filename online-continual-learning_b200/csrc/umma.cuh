@@ -43,6 +43,37 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);   // M / 16
 }
 
+// ---- MN-major operands (the contraction index K is the STRIDED one).  Measured on B200 (tools/umma_mn_probe*.py,
+// tests/test_gpu_umma.py): for kind::tf32 an MN-major operand must use layout type 1, SWIZZLE_128B_BASE32B -- with layout
+// type 2 (the 16-byte-base swizzle of the K-major tiles above) the instruction completes and writes ZEROS.  Element
+// (mn, k) of such an operand lives at
+//     start + (mn / 32) * LBO + (k / 4) * SBO + (k % 4) * 128 + (((mn % 32) / 8) ^ row) * 32 + (mn % 8) * 4   bytes,
+// row = bits 7..8 of the address: 32 consecutive M/N elements per 128-byte row, the four 32-byte chunks of a row XOR-ed
+// with the row index mod 4, one row per k, 4-row k groups SBO bytes apart, 32-element M/N blocks LBO bytes apart; one
+// kind::tf32 instruction (K = 8) reads two k groups.  With SBO = 512 the 8 k of an instruction are 8 consecutive rows:
+// exactly a "strip" (one 128-byte row of 32 channel slots per pixel position).  A weight gradient contracts over
+// positions, so activations and output gradients are both MN-major operands read in place -- and LBO = 128 makes M
+// block j the same strip shifted by j rows.  (CUTLASS: mma_sm100_desc.hpp LayoutType::SWIZZLE_128B_BASE32B,
+// Swizzle<2,5,2> o ((T,8,m),(4,k)).)
+// float offset of (row, 16-byte chunk c16) inside an array of 128-byte rows stored for such operands
+__device__ __forceinline__ int sw128b32_offset_f32(int row, int c16) {
+  return row * 32 + ((((c16 >> 1) ^ (row & 3)) << 3) | ((c16 & 1) << 2));
+}
+__device__ __forceinline__ uint64_t make_smem_desc_mn_b32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes = 512) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);           // start address
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // leading byte offset: next 32-element M/N block
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;     // stride byte offset: next 4-row K group
+  d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)
+  d |= (uint64_t)1 << 61;                               // layout type: SWIZZLE_128B_BASE32B
+  return d;
+}
+// kind::tf32 instruction descriptor with A and / or B MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t make_idesc_tf32_major(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- TMEM allocation (whole warp)
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_dst)),
