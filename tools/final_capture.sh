@@ -10,6 +10,6 @@ timeout 900 python bench.py --gpus 1 --steps 20 --warmup 3 > gpurun_out/bench_${
 timeout 900 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > gpurun_out/bench_${R}_reference.json 2> gpurun_out/bench_${R}_reference.err; cat gpurun_out/bench_${R}_reference.json | cut -c1-300
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1800 -c 1100 --csv \
     --log-file gpurun_out/launches_${R}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_${R}.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'conv_tcp_kernel|wgrad_kernel|knn_sv_kernel' \
-    -s 150 -c 6 -f -o gpurun_out/prof_${R} python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${R}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'conv_tcp_kernel|wgrad_tc_kernel|knn_sv_kernel' \
+    -s 400 -c 8 -f -o gpurun_out/prof_${R} python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${R}.log 2>&1
 ls -la gpurun_out | tail -6
