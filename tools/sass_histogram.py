@@ -22,7 +22,7 @@ def demangle(names):
 
 
 def main():
-    print('# r02 SASS opcode histograms (cuobjdump -sass on online-continual-learning_b200/build/*.o, sm_100a)\n')
+    print('# SASS opcode histograms (cuobjdump -sass on online-continual-learning_b200/build/*.o, sm_100a)\n')
     print('Counts are static instruction counts per kernel; `UTCHMMA` = tcgen05.mma, `LDTM` = tcgen05.ld, `UBLKCP` = '
           'cp.async.bulk (TMA 1-D bulk copy), `UTMALDG` = cp.async.bulk.tensor (none: operands that need a layout change are '
           'staged by loader warps, see DESIGN.md section 5), `SYNCS` = mbarrier ops, `LDGSTS` = cp.async.\n')
