@@ -268,13 +268,17 @@ int b200ocl_conv_selftest(const float* x, const float* w_oihw, float* out, int N
 int b200ocl_selftest_umma_window(const float* P, const float* B, float* D, int rows, int start_row, int sbo_rows,
                                  int base_off_mode, int N, int* status, void* stream);
 
-/* MN-major variant: both operands are windows into strips of 128-byte rows (32 fp32 per row), the contraction runs over
- * rows: D[32 j + c][32 q + n] = sum_{t < 8 ksteps} PA[a_row0 + j a_lbo_rows + t][c] * PB[b_row0 + q b_lbo_rows + t][n],
- * single TF32 pass.  a_lbo_rows = 1 (M block j = the strip shifted by j rows) is what the tensor-core weight gradient
- * relies on. */
+/* MN-major variant: both operands are windows into strips of 128-byte rows (32 fp32 per row, stored with the 32-byte-base
+ * 128-byte swizzle), the contraction runs over rows:
+ *   D[32 j + c][32 q + n] = sum_{g < 2 ksteps} sum_{t < 4} PA[a_row0 + j a_lbo_rows + g a_sbo_rows + t][c]
+ *                                                        * PB[b_row0 + q b_lbo_rows + g b_sbo_rows + t][n],   single TF32 pass.
+ * layout_type 1 = SWIZZLE_128B_BASE32B, what kind::tf32 needs for MN-major operands; layout_type 2 = SWIZZLE_128B, kept
+ * reachable because of what it does on B200: the instruction completes and D is all zeros (tests/test_gpu_umma.py).
+ * a_lbo_rows = 1, a_sbo_rows = 4 (M block j = the strip shifted by j rows, K over 8 consecutive rows) is what the
+ * tensor-core weight gradient relies on. */
 int b200ocl_selftest_umma_mn(const float* PA, const float* PB, float* D, int rows_a, int rows_b, int a_row0, int a_lbo_rows,
-                             int a_sbo_rows, int b_row0, int b_lbo_rows, int b_sbo_rows, int ksteps, int N, int* status,
-                             void* stream);
+                             int a_sbo_rows, int b_row0, int b_lbo_rows, int b_sbo_rows, int ksteps, int N, int layout_type,
+                             int* status, void* stream);
 
 /* Weight gradient of one 3x3 stride-1 pad-1 convolution through the tcgen05 kernel (wgrad_tc.cu), NHWC fp32 inputs,
  * dw in OIHW: the cuDNN weight-gradient call behind loss.backward() for nn.Conv2d (models/resnet.py:11-12).  Exists so

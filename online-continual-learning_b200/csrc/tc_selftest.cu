@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128) umma_window_kernel(const float* __restric
 __global__ void __launch_bounds__(128) umma_mn_kernel(const float* __restrict__ PA, const float* __restrict__ PB,
                                                       float* __restrict__ D, int rows_a, int rows_b, int a_row0,
                                                       int a_lbo_rows, int a_sbo_rows, int b_row0, int b_lbo_rows, int b_sbo_rows,
-                                                      int ksteps, int N, int* __restrict__ status) {
+                                                      int ksteps, int N, int layout_type, int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* sA = reinterpret_cast<float*>(smem_raw);
   float* sB = sA + (size_t)((rows_a + 7) / 8 * 8) * 32;
@@ -210,9 +210,12 @@ __global__ void __launch_bounds__(128) umma_mn_kernel(const float* __restrict__ 
                                                     (uint32_t)a_sbo_rows * 128u);
     const uint64_t dB = umma::make_smem_desc_mn_b32(umma::smem_u32(sB) + (uint32_t)b_row0 * 128u, (uint32_t)b_lbo_rows * 128u,
                                                     (uint32_t)b_sbo_rows * 128u);
+    // layout_type 2 (the 16-byte-base SWIZZLE_128B of the K-major tiles) is kept reachable to document the measured
+    // behaviour: the instruction completes and D is all zeros
+    const uint64_t lt = (layout_type == 2) ? (((uint64_t)1 << 61) ^ ((uint64_t)2 << 61)) : 0;
     for (int k = 0; k < ksteps; ++k) {
       const uint64_t adv_a = (uint64_t)(k * 2 * a_sbo_rows * 128 >> 4), adv_b = (uint64_t)(k * 2 * b_sbo_rows * 128 >> 4);
-      umma::mma_tf32_ss(tmem, dA + adv_a, dB + adv_b, idesc, k > 0 ? 1u : 0u);
+      umma::mma_tf32_ss(tmem, (dA + adv_a) ^ lt, (dB + adv_b) ^ lt, idesc, k > 0 ? 1u : 0u);
     }
     umma::mma_commit(&mbar);
   }
@@ -239,11 +242,12 @@ __global__ void __launch_bounds__(128) umma_mn_kernel(const float* __restrict__ 
 
 extern "C" int b200ocl_selftest_umma_mn(const float* PA, const float* PB, float* D, int rows_a, int rows_b, int a_row0,
                                         int a_lbo_rows, int a_sbo_rows, int b_row0, int b_lbo_rows, int b_sbo_rows, int ksteps,
-                                        int N, int* status, void* stream_) {
+                                        int N, int layout_type, int* status, void* stream_) {
   using namespace b200ocl;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200OCL_CHECK_ARG(PA && PB && D && status, "null pointer");
-  B200OCL_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && ksteps >= 1 && ksteps <= 64, "need N in [16,256] %16, 1 <= ksteps <= 64");
+  B200OCL_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && ksteps >= 1 && ksteps <= 64 && (layout_type == 1 || layout_type == 2),
+                    "need N in [16,256] %16, 1 <= ksteps <= 64, layout_type 1 or 2");
   B200OCL_CHECK_ARG(rows_a > 0 && rows_b > 0 && rows_a + rows_b <= 1600 && a_row0 >= 0 && b_row0 >= 0 && a_lbo_rows >= 1 &&
                         b_lbo_rows >= 1 && a_sbo_rows >= 1 && b_sbo_rows >= 1 &&
                         a_row0 + 3 * a_lbo_rows + (2 * ksteps - 1) * a_sbo_rows + 4 <= rows_a &&
@@ -252,7 +256,7 @@ extern "C" int b200ocl_selftest_umma_mn(const float* PA, const float* PB, float*
   const size_t smem = (size_t)((rows_a + 7) / 8 * 8 + (rows_b + 7) / 8 * 8) * 32 * sizeof(float) + 1024;
   B200OCL_CUDA(cudaFuncSetAttribute(umma_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_mn_kernel<<<1, 128, smem, stream>>>(PA, PB, D, rows_a, rows_b, a_row0, a_lbo_rows, a_sbo_rows, b_row0, b_lbo_rows, b_sbo_rows,
-                                           ksteps, N, status);
+                                           ksteps, N, layout_type, status);
   B200OCL_LAUNCHED();
   return B200OCL_OK;
 }

@@ -43,8 +43,8 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);   // M / 16
 }
 
-// ---- MN-major operands (the contraction index K is the STRIDED one).  Measured on B200 (tools/umma_mn_probe*.py,
-// tests/test_gpu_umma.py): for kind::tf32 an MN-major operand must use layout type 1, SWIZZLE_128B_BASE32B -- with layout
+// ---- MN-major operands (the contraction index K is the STRIDED one).  Measured on B200 with one-hot probes
+// (tests/test_gpu_umma.py keeps the result reproducible): for kind::tf32 an MN-major operand must use layout type 1, SWIZZLE_128B_BASE32B -- with layout
 // type 2 (the 16-byte-base swizzle of the K-major tiles above) the instruction completes and writes ZEROS.  Element
 // (mn, k) of such an operand lives at
 //     start + (mn / 32) * LBO + (k / 4) * SBO + (k % 4) * 128 + (((mn % 32) / 8) ^ row) * 32 + (mn % 8) * 4   bytes,

@@ -56,7 +56,7 @@ def test_umma_3xtf32_is_fp32_grade(N, K):
     assert e3 < 1.2e-8 * K + 1e-6, (e3, fp32)
 
 
-def run_mn(PA, PB, a_row0, a_lbo, a_sbo, b_row0, b_lbo, b_sbo, ksteps, N):
+def run_mn(PA, PB, a_row0, a_lbo, a_sbo, b_row0, b_lbo, b_sbo, ksteps, N, layout_type=1):
     from b200ocl import _native
     from b200ocl.ops import _stream
     lib = _native.lib()
@@ -64,7 +64,7 @@ def run_mn(PA, PB, a_row0, a_lbo, a_sbo, b_row0, b_lbo, b_sbo, ksteps, N):
     d = torch.full((128, N), float('nan'), device='cuda')
     status = torch.full((1,), -1, dtype=torch.int32, device='cuda')
     rc = lib.b200ocl_selftest_umma_mn(a.data_ptr(), b.data_ptr(), d.data_ptr(), PA.shape[0], PB.shape[0], a_row0, a_lbo, a_sbo,
-                                      b_row0, b_lbo, b_sbo, ksteps, N, status.data_ptr(), _stream())
+                                      b_row0, b_lbo, b_sbo, ksteps, N, layout_type, status.data_ptr(), _stream())
     _native.check(rc, 'b200ocl_selftest_umma_mn')
     torch.cuda.synchronize()
     assert int(status) == 0, 'MMA completion barrier timed out'
@@ -110,3 +110,18 @@ def test_umma_mn_major_strips(a_row0, a_lbo, a_sbo, b_row0, b_lbo, b_sbo, ksteps
     bad = np.argwhere(D != ref)
     assert bad.size == 0, ('first mismatches (row, col):', bad[:6].tolist(), 'mismatching rows:', sorted(set(bad[:, 0].tolist()))[:40],
                            'cols:', sorted(set(bad[:, 1].tolist()))[:40])
+
+
+def test_umma_mn_major_needs_the_32_byte_base_swizzle():
+    """Measured behaviour this stack builds on: with layout type 2 (SWIZZLE_128B, 16-byte base -- the type of the K-major
+    tiles) a kind::tf32 instruction with MN-major operands completes and leaves D all zeros; layout type 1
+    (SWIZZLE_128B_BASE32B) is the one that reads the operands."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    rs = np.random.RandomState(5)
+    PA = (rs.randint(1, 9, (64, 32)) / 8.0).astype(np.float32)
+    PB = (rs.randint(1, 9, (64, 32)) / 8.0).astype(np.float32)
+    D2 = run_mn(PA, PB, 0, 8, 4, 0, 8, 4, 1, 32, layout_type=2)
+    assert not D2.any(), 'layout type 2 now reads MN-major tf32 operands: revisit umma.cuh'
+    D1 = run_mn(PA, PB, 0, 8, 4, 0, 8, 4, 1, 32, layout_type=1)
+    np.testing.assert_array_equal(D1, mn_reference(PA, PB, 0, 8, 4, 0, 8, 4, 1, 32))
