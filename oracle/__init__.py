@@ -15,9 +15,12 @@ section 4), so the pin is the reference itself, executed in the build container:
 ``/root/reference`` (with the three optional-import stubs of SURVEY.md Appendix
 B), runs them on seeded inputs and writes ``tests/golden/*.npz``;
 ``tests/test_oracle_golden.py`` checks every oracle function against those
-files.  Two things stay "parity unpinned" (SURVEY.md section 8c): the SCR
-augmentation arithmetic (kornia 0.4.1 is not in the image and not vendored) and
-anything that depends on the exact conv/BN kernels of the pinned torch 1.7.1.
+files (`gss.npz` for oracle/gss.py).  Two things stay "parity unpinned" (SURVEY.md
+section 8c): the DEFINITION of the SCR augmentation pipeline (kornia 0.4.1 is not in the
+image and not vendored; oracle/augment.py restates its published formulas and is checked
+against torch's grid_sample and the standard library's colorsys instead,
+tests/test_oracle_augment.py) and anything that depends on the exact conv/BN kernels of
+the pinned torch 1.7.1.
 
 Every function cites the reference file:line it restates.
 """
