@@ -61,8 +61,8 @@ def import_reference(path=None):
 
 
 def _torch2_compat():
-    """The reference pins torch 1.7.1 (requirements.txt:2).  Under torch >= 2 ONE statement of its GPU path
-    raises: aser_update.py:102 indexes the CPU index tensor that random_retrieve returns
+    """The reference pins torch 1.7.1 (requirements.txt:2).  Under torch >= 2 two statements of its GPU path
+    raise (the second is handled further down): aser_update.py:102 indexes the CPU index tensor that random_retrieve returns
     (buffer_utils.py:17, torch.from_numpy) with a CUDA tensor.  The shim wraps the `random_retrieve` name
     bound in utils.buffer.aser_update so that the returned indices live on the buffer's device -- same
     values, same numpy draw, no file of the reference is edited.  It is a no-op on the CPU."""
